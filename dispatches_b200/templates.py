@@ -1,0 +1,218 @@
+"""LP templates of the reference's price-taker flowsheets (reduced / presolved forms).
+
+Each builder mirrors one reference model builder and keeps the reference's Var names for the columns
+that survive presolve, so results can be read back by name (record_results, wind_battery_LMP.py:272-325).
+
+Presolve done here once per template (the reference leaves it to CBC on every LP):
+  * arcs / ports (w = z, q = i, E = 4P ...) substituted away,
+  * fixed Vars become constants, constant lower bounds are shifted to 0,
+  * never-binding rows dropped (battery ramp <= 1e8, wind_battery_LMP.py:139-142; nameplate bounds 1e8/1e9),
+  * model-level capacity Vars sit at their fixed block values (their cost coefficients are positive),
+  * link / periodic equalities substituted (s0[t+1] := s[t]).
+
+Parameter conventions (LPTemplate.instantiate / solver.solve_batch):
+  wind_battery(T):        cparams = lmp[T] ($/MWh);  rparams = [wind_kw*cf_0 .. wind_kw*cf_{T-1}, batt_kw, wind_kw]
+  wind_battery_pem(T):    cparams = [lmp[T], h2_price];  rparams = [wind_kw*cf_t (T), batt_kw, wind_kw, pem_kw]
+  nuclear(T):             cparams = lmp[T];  rparams = [] (design constants baked in)
+  fossil_surrogate(T):    cparams = lmp[T];  rparams = []
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .lp_template import LPTemplate, TemplateBuilder
+
+# ---- constants of load_parameters.py:24-121 (wind_battery_cost_parameter.json: "moderate", 2023, 4-h)
+WIND_CAP_COST = 1308.0
+WIND_OP_COST = 41.78
+BATT_OP_COST = 31.39
+BATT_CAP_COST_KW = 236.365
+BATT_CAP_COST_KWH = 254.835
+PEM_CAP_COST = 1200.0
+PEM_OP_COST = 0.03 * PEM_CAP_COST
+PEM_VAR_COST = 0.0
+H2_MOLS_PER_KG = 500.0
+DURATION = 4.0
+ETA_C = ETA_D = 0.95                      # RE_flowsheet.py:151-152
+DEGRADATION = 1e-4                        # battery.py:91-95
+PEM_ELEC_TO_MOL = 0.00275984              # RE_flowsheet.py:131
+PA = ((1 + 0.08) ** 30 - 1) / (0.08 * (1 + 0.08) ** 30)     # load_parameters.py:119-121
+
+
+def wind_battery(T: int, extant_wind: bool = True) -> LPTemplate:
+    """wind_battery_optimize with design_opt=False (wind_battery_LMP.py:172-267; sweep mode of
+    run_pricetaker_wind_battery.py:37-58).  Objective = -NPV*1e-5 (:264)."""
+    iP, iW = T, T + 1
+    B = TemplateBuilder(f"wind_battery_T{T}", Pc=T, Pr=T + 2)
+    ann = 52.0 / (T / 168.0)
+    k_rev = -1e-5 * PA * ann * 1e-3
+    g, i, o, s, e = {}, {}, {}, {}, {}
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        g[t] = B.var(p + "splitter.grid_elec[0]")
+        i[t] = B.var(p + "battery.elec_in[0]", ub=(0.0, {iP: 1.0}))           # battery.py:159-161
+        o[t] = B.var(p + "battery.elec_out[0]", ub=(0.0, {iP: 1.0}))          # battery.py:163-165
+        # periodic s[T-1] = s0[0] = 0 (:48, :206)  ->  the last state of charge is the constant 0
+        s[t] = B.var(p + "battery.state_of_charge[0]", fix=(0.0 if t == T - 1 else None))
+        e[t] = B.var(p + "battery.energy_throughput[0]")
+        B.cost(g[t], (0.0, {t: k_rev})); B.cost(o[t], (0.0, {t: k_rev}))       # :235-237
+    for t in range(T):
+        row = {s[t]: 1.0, i[t]: -ETA_C, o[t]: 1.0 / ETA_D}                     # battery.py:145-149
+        if t > 0:
+            row[s[t - 1]] = -1.0                                              # link :33
+        B.eq(f"soc[{t}]", row)
+        row = {e[t]: 1.0, i[t]: -0.5, o[t]: -0.5}                              # battery.py:151-153
+        if t > 0:
+            row[e[t - 1]] = -1.0                                              # link :34
+        B.eq(f"throughput[{t}]", row)
+        B.le(f"soc_bound[{t}]", {s[t]: 1.0, e[t]: DEGRADATION}, (0.0, {iP: DURATION}))   # battery.py:155-157
+        B.le(f"wind[{t}]", {g[t]: 1.0, i[t]: 1.0}, (0.0, {t: 1.0}))           # wind_power.py:120-122 + splitter
+    cap = BATT_CAP_COST_KW + BATT_CAP_COST_KWH * DURATION
+    B.obj_const((0.0, {iP: 1e-5 * (cap + PA * ann * T * BATT_OP_COST / 8760.0),
+                       iW: 1e-5 * ((0.0 if extant_wind else WIND_CAP_COST) + PA * ann * T * WIND_OP_COST / 8760.0)}))
+    B.meta.update(kind="wind_battery", T=T, ann=ann)
+    return B.build()
+
+
+def wind_battery_rparams(T, cf, wind_mw, batt_mw, pem_mw=None):
+    """rparams rows for wind_battery / wind_battery_pem: cf [N,T] or [T]; sizes scalar or [N]."""
+    cf = np.atleast_2d(np.asarray(cf, float))
+    N = cf.shape[0]
+    W = np.broadcast_to(np.asarray(wind_mw, float) * 1e3, (N,))
+    P = np.broadcast_to(np.asarray(batt_mw, float) * 1e3, (N,))
+    cols = [cf * W[:, None], P[:, None], W[:, None]]
+    if pem_mw is not None:
+        cols.append(np.broadcast_to(np.asarray(pem_mw, float) * 1e3, (N,))[:, None])
+    return np.ascontiguousarray(np.concatenate(cols, axis=1))
+
+
+def wind_battery_pem(T: int, with_battery: bool = True, extant_wind: bool = True) -> LPTemplate:
+    """wind_battery_pem_optimize with design_opt=False (wind_battery_PEM_LMP.py:180-298).
+
+    Differences from wind_battery: PEM electricity column with H2 revenue (:276), only the initial energy
+    throughput is fixed (:217) so the state of charge is periodic (s0[0] = s[T-1], a cyclic link), and
+    run_pricetaker_wind_PEM.py:37-41 sweeps with batt_mw = 0 (``with_battery=False`` drops the battery
+    columns instead of bounding them by 0)."""
+    iP, iW, iPem = T, T + 1, T + 2
+    ih2 = T
+    B = TemplateBuilder(f"wind_battery_pem_T{T}" + ("" if with_battery else "_nobatt"), Pc=T + 1, Pr=T + 3)
+    ann = 52.0 / (T / 168.0)
+    k_rev = -1e-5 * PA * ann * 1e-3
+    k_h2 = -1e-5 * PA * ann * PEM_ELEC_TO_MOL / H2_MOLS_PER_KG * 3600.0
+    g, i, o, s, e, pe = {}, {}, {}, {}, {}, {}
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        g[t] = B.var(p + "splitter.grid_elec[0]")
+        pe[t] = B.var(p + "pem.electricity[0]", ub=(0.0, {iPem: 1.0}))         # :239
+        B.cost(g[t], (0.0, {t: k_rev}))
+        B.cost(pe[t], (1e-5 * PA * ann * PEM_VAR_COST, {ih2: k_h2}))            # :276, pem var cost :268
+        if with_battery:
+            i[t] = B.var(p + "battery.elec_in[0]", ub=(0.0, {iP: 1.0}))
+            o[t] = B.var(p + "battery.elec_out[0]", ub=(0.0, {iP: 1.0}))
+            s[t] = B.var(p + "battery.state_of_charge[0]")
+            e[t] = B.var(p + "battery.energy_throughput[0]")
+            B.cost(o[t], (0.0, {t: k_rev}))
+    for t in range(T):
+        wind_row = {g[t]: 1.0, pe[t]: 1.0}
+        if with_battery:
+            wind_row[i[t]] = 1.0
+            row = {s[t]: 1.0, i[t]: -ETA_C, o[t]: 1.0 / ETA_D}
+            row[s[(t - 1) % T]] = row.get(s[(t - 1) % T], 0.0) - 1.0            # link + periodic (cyclic)
+            B.eq(f"soc[{t}]", row)
+            row = {e[t]: 1.0, i[t]: -0.5, o[t]: -0.5}
+            if t > 0:
+                row[e[t - 1]] = -1.0
+            B.eq(f"throughput[{t}]", row)
+            B.le(f"soc_bound[{t}]", {s[t]: 1.0, e[t]: DEGRADATION}, (0.0, {iP: DURATION}))
+        B.le(f"wind[{t}]", wind_row, (0.0, {t: 1.0}))
+    cap = BATT_CAP_COST_KW + BATT_CAP_COST_KWH * DURATION
+    om = {iW: 1e-5 * ((0.0 if extant_wind else WIND_CAP_COST) + PA * ann * T * WIND_OP_COST / 8760.0),
+          iPem: 1e-5 * (PEM_CAP_COST + PA * ann * T * PEM_OP_COST / 8760.0)}
+    om[iP] = 1e-5 * (cap + PA * ann * T * BATT_OP_COST / 8760.0)
+    B.obj_const((0.0, om))
+    B.meta.update(kind="wind_battery_pem", T=T, ann=ann, with_battery=with_battery)
+    return B.build()
+
+
+# ---------------------------------------------------------------------------------------------
+MW_H2 = 2.016e-3
+NUC_PEM_ELEC_TO_MOL = 0.002527406          # nuclear_flowsheet.py:269
+
+
+def nuclear(T: int = 48, np_capacity=500.0, pem_capacity=100.0, tank_capacity=5000.0,
+            h2_demand=0.35, h2_price=4.0) -> LPTemplate:
+    """create_multiperiod_nuclear_model (nuclear_flowsheet_multiperiod_class.py:72-155) as a price-taker LP:
+    min sum_t [ operating_cost_t - lmp_t * np_to_grid_t * 1e-3 ]  (operating_cost :149-153)."""
+    E = np_capacity * 1e3
+    B = TemplateBuilder(f"nuclear_T{T}", Pc=T, Pr=0)
+    xp, u, H = {}, {}, {}
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        xp[t] = B.var(p + "pem.electricity[0]", ub=pem_capacity * 1e3)          # nuclear_flowsheet.py:137-138
+        u[t] = B.var(p + "h2_tank.outlet_to_pipeline.flow_mol[0]", ub=h2_demand / MW_H2)   # …_class.py:140-141
+        # tank_holdup[t] is tank_holdup_previous[t+1] (link :47-49) whose ub is tank_capacity/mw
+        # (nuclear_flowsheet.py:155-156); the last holdup has no successor, hence no upper bound
+        H[t] = B.var(p + "h2_tank.tank_holdup[0]", ub=(tank_capacity / MW_H2 if t < T - 1 else None))
+        # np_to_grid = E - xp  ->  -lmp*1e-3*(E - xp)
+        B.cost(xp[t], (1e-3 * 1.3, {t: 1e-3}))
+        B.cost(H[t], MW_H2 * 0.01)
+        B.cost(u[t], -MW_H2 * 3600.0 * h2_price)
+        B.ocmap[t] += -1e-3 * E
+        B.obj_const(E * 1e-3 * 2.3)
+    for t in range(T):
+        row = {H[t]: 1.0, xp[t]: -3600.0 * NUC_PEM_ELEC_TO_MOL, u[t]: 3600.0}   # hydrogen_tank_simplified.py:177-184
+        if t > 0:
+            row[H[t - 1]] = -1.0
+        B.eq(f"tank_balance[{t}]", row)
+    B.meta.update(kind="nuclear", T=T, E=E)
+    return B.build()
+
+
+# ---------------------------------------------------------------------------------------------
+FOSSIL = dict(p_lo=283.0, p_hi=436.0, pprev_lo=284.0, pprev_hi=466.0, hx_lo=10.0, hx_hi=200.0, ramp=60.0,
+              salt_total=6739292.0, hot_init=75000.0 + 1103053.48, pprev0=447.66,
+              kc=6.5, kd=7.0, eta_c=0.40, eta_d=0.38, fuel=22.0, fixed=6.0)
+
+
+def fossil_surrogate(T: int = 168, par=None) -> LPTemplate:
+    """STRUCTURE-ONLY linear surrogate of the ultra-supercritical plant + molten-salt storage price-taker
+    (multiperiod_integrated_storage_usc.py:49-54,75-164,334-342; pricetaker_with_…usc.py:88-107).  The
+    reference path is an NLP (IAPWS-95 steam cycle); only its linear inter-period structure is kept --
+    parity unpinned, see DESIGN.md."""
+    P = dict(FOSSIL); P.update(par or {})
+    B = TemplateBuilder(f"fossil_surrogate_T{T}", Pc=T, Pr=0)
+    pw, c, d, h = {}, {}, {}, {}
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        lo = max(P["p_lo"], P["pprev_lo"]) if t < T - 1 else P["p_lo"]         # P[t] is previous_power[t+1]
+        pw[t] = B.var(p + "plant_power_out[0]", lb=lo, ub=min(P["p_hi"], P["pprev_hi"]))
+        c[t] = B.var(p + "hxc.heat_duty[0]", lb=P["hx_lo"], ub=P["hx_hi"])
+        d[t] = B.var(p + "hxd.heat_duty[0]", lb=P["hx_lo"], ub=P["hx_hi"])
+        h[t] = B.var(p + "salt_inventory_hot", ub=P["salt_total"], fix=(P["hot_init"] if t == T - 1 else None))
+        B.cost(pw[t], (P["fuel"], {t: -1.0}))
+        B.cost(c[t], (0.0, {t: P["eta_c"]}))
+        B.cost(d[t], (0.0, {t: -P["eta_d"]}))
+        B.obj_const(P["fixed"])
+    for t in range(T):
+        hprev = {h[t - 1]: 1.0} if t > 0 else {}
+        hprev_const = 0.0 if t > 0 else P["hot_init"]
+        row = {h[t]: 1.0, c[t]: -3600.0 * P["kc"], d[t]: 3600.0 * P["kd"]}
+        for j, vv in hprev.items():
+            row[j] = -vv
+        B.eq(f"hot_balance[{t}]", row, hprev_const)
+        row = {d[t]: 3600.0 * P["kd"]}
+        for j, vv in hprev.items():
+            row[j] = -vv
+        B.le(f"discharge_limit[{t}]", row, hprev_const)
+        row = {c[t]: 3600.0 * P["kc"]}
+        for j, vv in hprev.items():
+            row[j] = vv
+        B.le(f"charge_limit[{t}]", row, P["salt_total"] - hprev_const)
+        if t > 0:
+            B.le(f"ramp_up[{t}]", {pw[t]: 1.0, pw[t - 1]: -1.0}, P["ramp"])
+            B.le(f"ramp_down[{t}]", {pw[t - 1]: 1.0, pw[t]: -1.0}, P["ramp"])
+        else:
+            B.le(f"ramp_up[{t}]", {pw[t]: 1.0}, P["ramp"] + P["pprev0"])
+            B.le(f"ramp_down[{t}]", {pw[t]: -1.0}, P["ramp"] - P["pprev0"])
+    B.meta.update(kind="fossil_surrogate", T=T)
+    return B.build()

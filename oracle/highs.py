@@ -1,0 +1,88 @@
+"""CPU ORACLE (test infrastructure -- NOT product code).
+
+Solves oracle.lp_models.RawLP instances with scipy's bundled HiGHS.  The reference hands the same
+LPs to CBC (wind_battery_LMP.py:266-267, wind_battery_PEM_LMP.py:296-298), Gurobi
+(nuclear_case/report/price_taker_analysis.py:365,403) or IPOPT; none of those is installable here
+(SURVEY.md §8c).  Any exact LP solver returns the same optimal objective, so HiGHS dual simplex
+(vertex solution, ~1e-16 relative objective agreement with HiGHS-IPM) is the accuracy oracle and the
+timed CPU baseline ("port").
+"""
+from __future__ import annotations
+
+import dataclasses
+import multiprocessing as mp
+import os
+import time
+
+import numpy as np
+from scipy.optimize import linprog
+
+from . import lp_models
+
+
+def solve(lp: lp_models.RawLP, method="highs-ds"):
+    bounds = np.column_stack([lp.lb, lp.ub])
+    bounds = [(None if not np.isfinite(l) else l, None if not np.isfinite(u) else u) for l, u in bounds]
+    res = linprog(lp.c, A_ub=lp.A_ub if lp.A_ub.shape[0] else None, b_ub=lp.b_ub if lp.A_ub.shape[0] else None,
+                  A_eq=lp.A_eq if lp.A_eq.shape[0] else None, b_eq=lp.b_eq if lp.A_eq.shape[0] else None,
+                  bounds=bounds, method=method)
+    if res.status != 0:
+        raise RuntimeError(f"HiGHS status {res.status}: {res.message}")
+    return float(res.fun + lp.c0), res.x
+
+
+# ---- batched loop used as the CPU baseline: the constraint data are built once per worker, only the
+# ---- cost vector (and, for design sweeps, rhs/bounds) is swapped per LP -- a generous baseline, the
+# ---- reference rebuilds the whole Pyomo model per LP.
+_W = {}
+
+
+def _init_worker(kind, kwargs):
+    _W["kind"], _W["kwargs"] = kind, kwargs
+
+
+def _build(kind, lmp, extra, kwargs):
+    if kind == "wind_battery":
+        cf, wind_mw, batt_mw = extra
+        return lp_models.wind_battery_raw(lmp, cf, wind_mw, batt_mw, **kwargs)
+    if kind == "nuclear":
+        return lp_models.nuclear_raw(lmp, **kwargs)
+    if kind == "fossil_surrogate":
+        return lp_models.fossil_surrogate_raw(lmp, **kwargs)
+    raise ValueError(kind)
+
+
+def _solve_chunk(args):
+    lmps, extras = args
+    kind, kwargs = _W["kind"], _W["kwargs"]
+    out = np.empty(len(lmps))
+    base = None
+    for k, lmp in enumerate(lmps):
+        extra = extras[k] if extras is not None else None
+        if base is None or extra is not None:
+            base, base_lmp = _build(kind, lmp, extra, kwargs), lmp
+            lp = base
+        else:       # same constraints, new cost vector only
+            lp = dataclasses.replace(base, c=lp_models.swap_lmp(base, base_lmp, lmp))
+        out[k], _ = solve(lp)
+    return out
+
+
+def solve_batch(kind, lmps, extras=None, kwargs=None, procs=None):
+    """Objective of every LP of a batch; ``procs`` worker processes (default: all host cores).
+    Returns (obj[N], seconds, procs)."""
+    kwargs = kwargs or {}
+    procs = procs or os.cpu_count() or 1
+    lmps = np.asarray(lmps, float)
+    N = lmps.shape[0]
+    chunks = np.array_split(np.arange(N), max(1, min(N, procs * 4)))
+    jobs = [(lmps[ix], None if extras is None else [extras[i] for i in ix]) for ix in chunks if ix.size]
+    t0 = time.perf_counter()
+    if procs == 1:
+        _init_worker(kind, kwargs)
+        outs = [_solve_chunk(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(procs, initializer=_init_worker, initargs=(kind, kwargs)) as pool:
+            outs = pool.map(_solve_chunk, jobs)
+    dt = time.perf_counter() - t0
+    return np.concatenate(outs), dt, procs

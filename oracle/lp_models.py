@@ -1,0 +1,379 @@
+"""CPU ORACLE (test infrastructure -- NOT product code; only tests/, bench.py's
+cpu_baseline / --impl reference leg and __graft_entry__.smoke() may import this).
+
+Raw, *un-presolved* restatements of the reference's price-taker LPs, shaped the
+way Pyomo would hand them to CBC/IPOPT: every Var of every cloned period block
+is a column (fixed Vars keep their column with lb == ub), every Constraint a
+row, linking / periodic equalities are explicit rows.  The product templates in
+``dispatches_b200/templates.py`` are *reduced* forms written independently; the
+parity tests compare one against the other through HiGHS and the CUDA solver.
+
+Reference equations restated here (file:line under /root/reference/dispatches):
+  unit_models/battery.py:69-165            battery Vars, bounds and 5 rows
+  unit_models/wind_power.py:99-122,178-183 electricity <= system_capacity*cf
+  unit_models/elec_splitter.py:107-117     electricity == sum(outlets)
+  unit_models/pem_electrolyzer.py:90-114   flow_mol == electricity*electricity_to_mol
+  case_studies/renewables_case/RE_flowsheet.py:69-87,138-157,387-396
+  case_studies/renewables_case/wind_battery_LMP.py:22-50,139-142,206-264
+  case_studies/renewables_case/wind_battery_PEM_LMP.py:217-294
+  case_studies/renewables_case/load_parameters.py:24-140
+  case_studies/nuclear_case/nuclear_flowsheet_multiperiod_class.py:36-155
+  case_studies/nuclear_case/nuclear_flowsheet.py:119-157,263-291
+  unit_models/hydrogen_tank_simplified.py:177-184
+  case_studies/fossil_case/ultra_supercritical_plant/storage/
+      multiperiod_integrated_storage_usc.py:49-54,75-164,334-342 (structure only)
+
+Parity pinning: see oracle/README.md -- the wind+PEM restatement is pinned to the
+reference's committed result tables (tests/golden/wind_pem_golden.json, made by
+tests/golden/make_golden.py); battery row semantics to the reference's unit-test
+known answers; the fossil surrogate is "parity unpinned".
+"""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+import scipy.sparse as sp
+
+INF = float("inf")
+
+# ---- constants restated from load_parameters.py:24-121 and wind_battery_cost_parameter.json
+# (scenario "moderate", year 2023, 4-h battery column)
+WIND_CAP_COST = 1308.0          # $/kW
+WIND_OP_COST = 41.78            # $/kW-yr
+BATT_OP_COST = 31.39            # $/kW-yr
+BATT_CAP_COST_KW = 236.365      # $/kW
+BATT_CAP_COST_KWH = 254.835     # $/kWh
+PEM_CAP_COST = 1200.0           # $/kW
+PEM_OP_COST = 0.03 * PEM_CAP_COST
+PEM_VAR_COST = 0.0
+H2_MOLS_PER_KG = 500.0
+DURATION = 4.0                  # hours of storage
+BATTERY_RAMP_RATE = 1e8
+ETA_C = 0.95
+ETA_D = 0.95
+DEGRADATION = 1.0 / 10000.0
+PEM_ELEC_TO_MOL = 0.00275984    # RE_flowsheet.py:131
+DISCOUNT, YEARS = 0.08, 30
+PA = ((1 + DISCOUNT) ** YEARS - 1) / (DISCOUNT * (1 + DISCOUNT) ** YEARS)
+
+
+@dataclasses.dataclass
+class RawLP:
+    """min c@x + c0  s.t.  A_eq x = b_eq, A_ub x <= b_ub, lb <= x <= ub."""
+    c: np.ndarray
+    c0: float
+    A_eq: sp.csr_matrix
+    b_eq: np.ndarray
+    A_ub: sp.csr_matrix
+    b_ub: np.ndarray
+    lb: np.ndarray
+    ub: np.ndarray
+    names: list
+    meta: dict
+
+    @property
+    def n(self):
+        return self.c.size
+
+
+class _Builder:
+    def __init__(self):
+        self.names, self.lb, self.ub, self.c = [], [], [], []
+        self.eq_rows, self.eq_rhs, self.ub_rows, self.ub_rhs = [], [], [], []
+        self.c0 = 0.0
+        self.lmp_terms = []
+
+    def var(self, name, lb=0.0, ub=INF, fix=None):
+        if fix is not None:
+            lb = ub = float(fix)
+        self.names.append(name)
+        self.lb.append(lb)
+        self.ub.append(ub)
+        self.c.append(0.0)
+        return len(self.names) - 1
+
+    def eq(self, coeffs, rhs=0.0):
+        self.eq_rows.append(coeffs)
+        self.eq_rhs.append(rhs)
+
+    def le(self, coeffs, rhs=0.0):
+        self.ub_rows.append(coeffs)
+        self.ub_rhs.append(rhs)
+
+    def cost(self, j, v):
+        self.c[j] += v
+
+    def cost_lmp(self, j, t, coef, lmp):
+        """cost entry coef*lmp[t] on column j; remembered so a batch loop can swap the LMP vector only."""
+        self.c[j] += coef * lmp[t]
+        self.lmp_terms.append((j, t, coef))
+
+    def _mat(self, rows):
+        n = len(self.names)
+        ri, ci, vv = [], [], []
+        for r, row in enumerate(rows):
+            for j, v in row.items():
+                ri.append(r); ci.append(j); vv.append(v)
+        return sp.csr_matrix((vv, (ri, ci)), shape=(len(rows), n))
+
+    def finish(self, meta):
+        meta = dict(meta, lmp_terms=self.lmp_terms)
+        return RawLP(np.array(self.c, float), float(self.c0), self._mat(self.eq_rows),
+                     np.array(self.eq_rhs, float), self._mat(self.ub_rows), np.array(self.ub_rhs, float),
+                     np.array(self.lb, float), np.array(self.ub, float), self.names, meta)
+
+
+def swap_lmp(lp: "RawLP", lmp_old, lmp_new):
+    """Cost vector of the same LP under another LMP signal (everything else is LMP-independent)."""
+    c = lp.c.copy()
+    d = np.asarray(lmp_new, float) - np.asarray(lmp_old, float)
+    for j, t, coef in lp.meta["lmp_terms"]:
+        c[j] += coef * d[t]
+    return c
+
+
+def _add(d, j, v):
+    d[j] = d.get(j, 0.0) + v
+
+
+# --------------------------------------------------------------------------------------
+# A.1 / A.2  wind + battery (+ PEM) price-taker
+# --------------------------------------------------------------------------------------
+def wind_battery_raw(lmp, cf, wind_mw, batt_mw, pem_mw=None, h2_price=2.0,
+                     design_opt=False, extant_wind=True, wind_mw_ub=10000.0):
+    """Raw LP of wind_battery_optimize (wind_battery_LMP.py:172-267) or, when ``pem_mw`` is not
+    None, of wind_battery_pem_optimize (wind_battery_PEM_LMP.py:180-298).
+
+    lmp [$/MWh], cf [-] have length T.  Objective = -NPV*1e-5 (:264 / :294).
+    design_opt: False | True | "PEM" (the reference's three modes).
+    """
+    lmp = np.asarray(lmp, float); cf = np.asarray(cf, float)
+    T = lmp.size
+    with_pem = pem_mw is not None
+    B = _Builder()
+    v = {}
+    free_batt = (design_opt is True)
+    free_wind = bool(design_opt) and not extant_wind
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        # wind_power.py:99-115 ; RE_flowsheet.py:86 fixes system_capacity
+        v["C", t] = B.var(p + "windpower.system_capacity", fix=None if free_wind else wind_mw * 1e3)
+        v["w", t] = B.var(p + "windpower.electricity[0]")
+        # elec_splitter.py:107-111
+        v["z", t] = B.var(p + "splitter.electricity[0]")
+        v["g", t] = B.var(p + "splitter.grid_elec[0]")
+        v["q", t] = B.var(p + "splitter.battery_elec[0]")
+        # battery.py:69-136 ; RE_flowsheet.py:154-156
+        batt_fix = None if free_batt else (0.0 if design_opt == "PEM" else batt_mw * 1e3)
+        v["P", t] = B.var(p + "battery.nameplate_power", ub=1e8, fix=batt_fix)
+        v["E", t] = B.var(p + "battery.nameplate_energy", ub=1e9)
+        v["s0", t] = B.var(p + "battery.initial_state_of_charge")
+        v["e0", t] = B.var(p + "battery.initial_energy_throughput")
+        v["i", t] = B.var(p + "battery.elec_in[0]")
+        v["o", t] = B.var(p + "battery.elec_out[0]")
+        v["s", t] = B.var(p + "battery.state_of_charge[0]")
+        v["e", t] = B.var(p + "battery.energy_throughput[0]")
+        if with_pem:
+            v["p", t] = B.var(p + "splitter.pem_elec[0]")
+            v["pe", t] = B.var(p + "pem.electricity[0]", lb=-INF)       # Reals, pem_electrolyzer.py:96-100
+            v["h", t] = B.var(p + "pem.outlet.flow_mol[0]", lb=-INF)
+        # rows
+        B.le({v["w", t]: 1.0, v["C", t]: -cf[t]})                       # wind_power.py:120-122
+        B.eq({v["w", t]: 1.0, v["z", t]: -1.0})                         # arc wind_to_splitter
+        row = {v["z", t]: 1.0, v["g", t]: -1.0, v["q", t]: -1.0}        # elec_splitter.py:115-117
+        if with_pem:
+            row[v["p", t]] = -1.0
+        B.eq(row)
+        B.eq({v["q", t]: 1.0, v["i", t]: -1.0})                         # arc splitter_to_battery
+        if with_pem:
+            B.eq({v["p", t]: 1.0, v["pe", t]: -1.0})                    # arc splitter_to_pem
+            B.eq({v["h", t]: 1.0, v["pe", t]: -PEM_ELEC_TO_MOL})        # pem_electrolyzer.py:111-114
+        B.eq({v["s", t]: 1.0, v["s0", t]: -1.0, v["i", t]: -ETA_C, v["o", t]: 1.0 / ETA_D})   # battery.py:145-149
+        B.eq({v["e", t]: 1.0, v["e0", t]: -1.0, v["i", t]: -0.5, v["o", t]: -0.5})            # battery.py:151-153
+        B.le({v["s", t]: 1.0, v["E", t]: -1.0, v["e", t]: DEGRADATION})                        # battery.py:155-157
+        B.le({v["i", t]: 1.0, v["P", t]: -1.0})                                                 # battery.py:159-161
+        B.le({v["o", t]: 1.0, v["P", t]: -1.0})                                                 # battery.py:163-165
+        B.eq({v["P", t]: DURATION, v["E", t]: -1.0})                                            # RE_flowsheet.py:155-156
+        B.le({v["s0", t]: 1.0, v["s", t]: -1.0}, BATTERY_RAMP_RATE)                             # wind_battery_LMP.py:139-140
+        B.le({v["s", t]: 1.0, v["s0", t]: -1.0}, BATTERY_RAMP_RATE)                             # :141-142
+    # linking t -> t+1 (wind_battery_LMP.py:32-36)
+    for t in range(T - 1):
+        B.eq({v["s", t]: 1.0, v["s0", t + 1]: -1.0})
+        B.eq({v["e", t]: 1.0, v["e0", t + 1]: -1.0})
+        B.eq({v["P", t]: 1.0, v["P", t + 1]: -1.0})
+    # periodic (:48-49)
+    B.eq({v["s", T - 1]: 1.0, v["s0", 0]: -1.0})
+    if T > 1:
+        B.eq({v["P", T - 1]: 1.0, v["P", 0]: -1.0})
+    # fixed initial conditions: wind_battery_LMP.py:206-207 fixes both; the PEM variant only e0 (:217)
+    B.lb[v["e0", 0]] = B.ub[v["e0", 0]] = 0.0
+    if not with_pem:
+        B.lb[v["s0", 0]] = B.ub[v["s0", 0]] = 0.0
+    # model-level capacities (:209-219)
+    Wc = B.var("wind_system_capacity", ub=wind_mw_ub * 1e3)
+    Bc = B.var("battery_system_capacity")
+    if with_pem and design_opt is not False and extant_wind:
+        B.lb[Wc] = B.ub[Wc] = wind_mw * 1e3                             # wind_battery_PEM_LMP.py:230-231
+    if with_pem:
+        Pc = B.var("pem_system_capacity", fix=(pem_mw * 1e3 if design_opt is False else None))
+    for t in range(T):
+        B.le({v["C", t]: 1.0, Wc: -1.0})
+        B.le({v["P", t]: 1.0, Bc: -1.0})
+        if with_pem:
+            B.le({v["pe", t]: 1.0, Pc: -1.0})
+    # objective  -NPV*1e-5
+    n_weeks = T / 168.0
+    ann = 52.0 / n_weeks
+    wind_cap = 0.0 if extant_wind else WIND_CAP_COST
+    npv = {}           # NPV as a linear form over columns
+    _add(npv, Wc, -wind_cap)
+    _add(npv, Bc, -(BATT_CAP_COST_KW + BATT_CAP_COST_KWH * DURATION))
+    if with_pem:
+        _add(npv, Pc, -PEM_CAP_COST)
+    for t in range(T):
+        B.cost_lmp(v["g", t], t, -1e-5 * PA * ann * 1e-3, lmp)
+        B.cost_lmp(v["o", t], t, -1e-5 * PA * ann * 1e-3, lmp)
+        _add(npv, Wc, -PA * ann * WIND_OP_COST / 8760.0)
+        _add(npv, Bc, -PA * ann * BATT_OP_COST / 8760.0)
+        if with_pem:
+            _add(npv, Pc, -PA * ann * PEM_OP_COST / 8760.0)
+            _add(npv, v["pe", t], -PA * ann * PEM_VAR_COST)
+            _add(npv, v["h", t], PA * ann * h2_price / H2_MOLS_PER_KG * 3600.0)
+    for j, val in npv.items():
+        B.cost(j, -val * 1e-5)
+    meta = dict(kind="wind_battery_pem" if with_pem else "wind_battery", T=T, v=v, Wc=Wc, Bc=Bc,
+                Pc=(Pc if with_pem else None), ann=ann, h2_price=h2_price)
+    return B.finish(meta)
+
+
+def wind_battery_report(lp: RawLP, x, lmp):
+    """Quantities the reference reads back (wind_battery_LMP.py:252-263, record_results :272-325;
+    wind_battery_PEM_LMP.py:300-330)."""
+    m = lp.meta; v = m["v"]; T = m["T"]; ann = m["ann"]
+    lam = np.asarray(lmp, float) * 1e-3
+    g = np.array([x[v["g", t]] for t in range(T)]); o = np.array([x[v["o", t]] for t in range(T)])
+    elec_rev = float(np.sum(lam * (g + o)))
+    out = dict(NPV=-(lp.c @ x + lp.c0) * 1e5, annual_elec_revenue=elec_rev * ann,
+               total_elec_output=float(np.sum(g + o)) * ann)
+    fixed = x[m["Wc"]] * WIND_OP_COST / 8760.0 + x[m["Bc"]] * BATT_OP_COST / 8760.0
+    h2_rev = 0.0
+    if m["Pc"] is not None:
+        h = np.array([x[v["h", t]] for t in range(T)])
+        h2_rev = float(np.sum(h)) * m["h2_price"] / H2_MOLS_PER_KG * 3600.0
+        fixed += x[m["Pc"]] * PEM_OP_COST / 8760.0
+        out["annual_rev_h2"] = h2_rev * ann
+        out["annual_rev_E"] = elec_rev * ann
+    out["annual_revenue"] = (elec_rev + h2_rev - fixed * T) * ann
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# A.3  nuclear + PEM + tank, 48-h dispatch (nuclear_flowsheet_multiperiod_class.py:72-155)
+# --------------------------------------------------------------------------------------
+MW_H2 = 2.016e-3
+NUC_PEM_ELEC_TO_MOL = 0.002527406    # nuclear_flowsheet.py:269
+
+
+def nuclear_raw(lmp, np_capacity=500.0, pem_capacity=100.0, tank_capacity=5000.0,
+                h2_demand=0.35, h2_price=4.0):
+    """Raw LP: max sum_t [ lmp_t * np_to_grid_t * 1e-3 - operating_cost_t ]  written as a minimisation.
+
+    Per block (nuclear_flowsheet.py:119-157, fixed values :263-291): splitter electricity fixed at
+    np_capacity*1e3 kW with split-fraction Vars (elec_splitter.py:119-129, linear because the inlet is fixed),
+    pem.electricity <= pem_capacity*1e3, flow = 0.002527406*electricity, simple tank balance with dt = 3600
+    (hydrogen_tank_simplified.py:177-184), turbine outlet fixed 0, pipeline flow <= h2_demand/mw,
+    tank_holdup_previous <= tank_capacity/mw, link holdup[t] -> holdup_previous[t+1], holdup_previous[0]=0.
+    Operating cost (…_class.py:149-153).
+    """
+    lmp = np.asarray(lmp, float); T = lmp.size
+    B = _Builder(); v = {}
+    E = np_capacity * 1e3
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        v["E", t] = B.var(p + "np_power_split.electricity[0]", fix=E)
+        v["fg", t] = B.var(p + "np_power_split.split_fraction[np_to_grid,0]", ub=1.0)
+        v["fp", t] = B.var(p + "np_power_split.split_fraction[np_to_pem,0]", ub=1.0)
+        v["xg", t] = B.var(p + "np_power_split.np_to_grid_elec[0]")
+        v["xs", t] = B.var(p + "np_power_split.np_to_pem_elec[0]")
+        v["xp", t] = B.var(p + "pem.electricity[0]", lb=-INF, ub=pem_capacity * 1e3)
+        v["f", t] = B.var(p + "pem.outlet.flow_mol[0]", lb=-INF)
+        v["fi", t] = B.var(p + "h2_tank.inlet.flow_mol[0]", lb=-INF)
+        v["Hp", t] = B.var(p + "h2_tank.tank_holdup_previous[0]", ub=tank_capacity / MW_H2)
+        v["H", t] = B.var(p + "h2_tank.tank_holdup[0]")
+        v["u", t] = B.var(p + "h2_tank.outlet_to_pipeline.flow_mol[0]", ub=h2_demand / MW_H2)
+        v["vt", t] = B.var(p + "h2_tank.outlet_to_turbine.flow_mol[0]", fix=0.0)
+        B.eq({v["E", t]: 1.0, v["xg", t]: -1.0, v["xs", t]: -1.0})            # sum of outlets
+        B.eq({v["xg", t]: 1.0, v["fg", t]: -E})                               # outlet = sf * E (E fixed)
+        B.eq({v["xs", t]: 1.0, v["fp", t]: -E})
+        B.eq({v["xs", t]: 1.0, v["xp", t]: -1.0})                             # arc np -> pem
+        B.eq({v["f", t]: 1.0, v["xp", t]: -NUC_PEM_ELEC_TO_MOL})
+        B.eq({v["f", t]: 1.0, v["fi", t]: -1.0})                              # arc pem -> tank
+        B.eq({v["H", t]: 1.0, v["Hp", t]: -1.0, v["fi", t]: -3600.0,
+              v["u", t]: 3600.0, v["vt", t]: 3600.0})
+        # objective (minimise cost - revenue)
+        B.cost_lmp(v["xg", t], t, -1e-3, lmp)
+        B.cost(v["E", t], 1e-3 * 2.3)
+        B.cost(v["xp", t], 1e-3 * 1.3)
+        B.cost(v["H", t], MW_H2 * 0.01)
+        B.cost(v["u", t], -MW_H2 * 3600.0 * h2_price)
+    for t in range(T - 1):
+        B.eq({v["H", t]: 1.0, v["Hp", t + 1]: -1.0})
+    B.lb[v["Hp", 0]] = B.ub[v["Hp", 0]] = 0.0
+    return B.finish(dict(kind="nuclear", T=T, v=v))
+
+
+# --------------------------------------------------------------------------------------
+# A.4  fossil USC + molten-salt storage: STRUCTURE-ONLY LP SURROGATE  (parity unpinned)
+# --------------------------------------------------------------------------------------
+FOSSIL = dict(
+    p_lo=283.0, p_hi=436.0,            # plant power bounds, multiperiod_integrated_storage_usc.py:49-50,75-80
+    pprev_lo=284.0, pprev_hi=466.0,    # previous_power bounds :51-54,89-94
+    hx_lo=10.0, hx_hi=200.0,           # storage duty bounds :82-86
+    ramp=60.0,                         # :125-135
+    salt_total=6739292.0,              # :98
+    hot_init=75000.0 + 1103053.48,     # hot tank starts near-empty + min level (:111-123, surrogate constant)
+    pprev0=447.66,                     # :114
+    # --- surrogate constants (OURS, not the reference's NLP): linear duty->salt-flow, duty->power, heat-rate cost
+    kc=6.5, kd=7.0,                    # kg/s of salt per MW of charge / discharge duty
+    eta_c=0.40, eta_d=0.38,            # MW of net power lost / gained per MW of duty
+    fuel=22.0, fixed=6.0,              # $/MWh of plant power ; $/h constant
+)
+
+
+def fossil_surrogate_raw(lmp, par=None):
+    """Linear surrogate of the USC + TES price-taker (pricetaker_with_multiperiod_integrated_storage_usc.py:69-156).
+    Keeps every *linear* inter-period piece of the reference and replaces the per-period steam-cycle NLP by
+    three linear maps (documented in FOSSIL).  Not comparable with the reference's IPOPT objective."""
+    P = dict(FOSSIL); P.update(par or {})
+    lmp = np.asarray(lmp, float); T = lmp.size
+    B = _Builder(); v = {}
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        v["P", t] = B.var(p + "plant_power_out[0]", lb=P["p_lo"], ub=P["p_hi"])
+        v["Pp", t] = B.var(p + "previous_power", lb=P["pprev_lo"], ub=P["pprev_hi"])
+        v["c", t] = B.var(p + "hxc.heat_duty[0]", lb=P["hx_lo"], ub=P["hx_hi"])
+        v["d", t] = B.var(p + "hxd.heat_duty[0]", lb=P["hx_lo"], ub=P["hx_hi"])
+        v["hp", t] = B.var(p + "previous_salt_inventory_hot", ub=P["salt_total"])
+        v["h", t] = B.var(p + "salt_inventory_hot", ub=P["salt_total"])
+        v["cp", t] = B.var(p + "previous_salt_inventory_cold", ub=P["salt_total"])
+        v["cl", t] = B.var(p + "salt_inventory_cold", ub=P["salt_total"])
+        B.le({v["P", t]: 1.0, v["Pp", t]: -1.0}, P["ramp"])                    # :125-135
+        B.le({v["Pp", t]: 1.0, v["P", t]: -1.0}, P["ramp"])
+        B.eq({v["h", t]: 1.0, v["hp", t]: -1.0, v["c", t]: -3600.0 * P["kc"], v["d", t]: 3600.0 * P["kd"]})   # :137-144
+        B.le({v["d", t]: 3600.0 * P["kd"], v["hp", t]: -1.0})                 # :146-151
+        B.le({v["c", t]: 3600.0 * P["kc"], v["cp", t]: -1.0})                 # :153-158
+        B.eq({v["h", t]: 1.0, v["cl", t]: 1.0}, P["salt_total"])              # :160-164
+        B.eq({v["hp", t]: 1.0, v["cp", t]: 1.0}, P["salt_total"])
+        # minimise -(lmp*net_power - opcost)
+        B.cost(v["P", t], P["fuel"])
+        B.cost_lmp(v["P", t], t, -1.0, lmp)
+        B.cost_lmp(v["c", t], t, P["eta_c"], lmp)
+        B.cost_lmp(v["d", t], t, -P["eta_d"], lmp)
+        B.c0 += P["fixed"]
+    for t in range(T - 1):                                                     # :334-342
+        B.eq({v["h", t]: 1.0, v["hp", t + 1]: -1.0})
+        B.eq({v["P", t]: 1.0, v["Pp", t + 1]: -1.0})
+    B.eq({v["h", T - 1]: 1.0, v["hp", 0]: -1.0})                               # periodic, pricetaker…:88-90
+    B.lb[v["hp", 0]] = B.ub[v["hp", 0]] = P["hot_init"]
+    B.lb[v["Pp", 0]] = B.ub[v["Pp", 0]] = P["pprev0"]
+    return B.finish(dict(kind="fossil_surrogate", T=T, v=v))
