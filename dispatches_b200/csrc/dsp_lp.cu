@@ -1,0 +1,769 @@
+// dsp_lp.cu -- batched primal-dual interior-point LP solver for sm_100a (B200).  C ABI: include/dsp_lp.h
+//
+// Replaces the per-scenario  SolverFactory("cbc").solve(m)  loop of the reference's price-taker sweeps
+// (wind_battery_LMP.py:266-267, wind_battery_PEM_LMP.py:296-298, price_taker_analysis.py:365-403) by one
+// launch that solves the whole scenario batch.
+//
+// Kernel `dsp_ipm_band_kernel`  (generic path, any template whose A*A' is banded):
+//   * one CTA per SM, persistent; one WARP per LP, problems handed out by an atomic ticket (iteration counts
+//     differ per LP);
+//   * the shared template (A in CSR and CSC, band assembly list) is staged once per CTA into shared memory with
+//     a TMA bulk copy (cp.async.bulk + mbarrier) when it fits, otherwise read through L2;
+//   * every per-problem vector and the band of M = A D A' live in shared memory for the whole solve;
+//     HBM traffic per LP is the parameter row in and (obj, status, iters [, x, y]) out;
+//   * FP64 throughout (cond(M) reaches 1e15 near convergence);
+//   * Mehrotra predictor-corrector; M is factorised once per iteration by a band LDL' (half bandwidth w),
+//     two band solves per iteration.  The numpy mirror of exactly this algorithm is oracle/ipm_numpy.py.
+#include "dsp_lp.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#define DSP_VERSION "dsp_lp 0.1 (sm_100a band-IPM)"
+
+namespace {
+
+constexpr int kMaxWarps = 16;
+constexpr int kMaxPairPasses = 4;          // w*w <= 128  ->  w <= 11 on the fast path
+constexpr double kGapFloor = 1e-4;         // scaled-objective floor of the relative gap test
+constexpr double kPivotRel = 1e-14;
+
+struct KParams {
+    // template
+    int m, n, nb, w, Pc, Pr, nnz, nasm;
+    const unsigned char *hot_g;   // hot blob in global memory
+    int hot_bytes;                // multiple of 16
+    int hot_in_smem;
+    const double *c0, *b0, *u0, *omap, *ocmap;
+    const int *cm_ptr, *cm_idx, *bm_ptr, *bm_idx, *um_ptr, *um_idx;
+    const double *cm_val, *bm_val, *um_val;
+    double o0;
+    // batch
+    long long N;
+    const double *cparams, *rparams;
+    long long rstride;
+    double tol, step_frac;
+    int max_iter;
+    double *obj, *x_out, *y_out;
+    int *status, *iters;
+    unsigned long long *ticket;
+    int prob_doubles;             // per-warp shared-memory doubles
+    int prob_off;                 // byte offset of the first per-warp region
+};
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS)
+__device__ __forceinline__ void tma_stage(void *dst, const void *src, int bytes, uint64_t *bar) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        // bulk copies are limited in size per instruction; issue in chunks
+        int off = 0;
+        while (off < bytes) {
+            int chunk = min(bytes - off, 32768);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32((char *)dst + off)), "l"((const char *)src + off), "r"(chunk), "r"(smem_u32(bar))
+                         : "memory");
+            off += chunk;
+        }
+    }
+    // every thread waits for phase 0 to complete
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(0)
+        : "memory");
+}
+
+struct Hot {   // views into the hot blob (shared or global)
+    const double *A_val, *At_val, *asm_val;
+    const int *A_ptr, *A_idx, *At_ptr, *At_idx, *asm_ptr, *asm_col;
+};
+
+__device__ __forceinline__ Hot hot_views(const unsigned char *base, const KParams &P) {
+    Hot h;
+    h.A_val = (const double *)base;
+    h.At_val = h.A_val + P.nnz;
+    h.asm_val = h.At_val + P.nnz;
+    h.A_ptr = (const int *)(h.asm_val + P.nasm);
+    h.A_idx = h.A_ptr + (P.m + 1);
+    h.At_ptr = h.A_idx + P.nnz;
+    h.At_idx = h.At_ptr + (P.n + 1);
+    h.asm_ptr = h.At_idx + P.nnz;
+    h.asm_col = h.asm_ptr + (P.m * (P.w + 1) + 1);
+    return h;
+}
+
+// ---- band LDL' of M (lower band, row-major Mb[i*(w+1)+k] = M[i][i-k]); on exit the diagonal slot holds
+// ---- 1/d_i (0 for a dropped pivot) and the off-diagonal slots the UNSCALED column entries L[i][i-k]*d_{i-k}.
+// ---- diag0[i] = M[i][i] before elimination (pivot test).  One warp.
+__device__ void band_factor(double *Mb, const double *diag0, int m, int w, int lane) {
+    const int W1 = w + 1;
+    const int npairs = w * w;
+    int pr[kMaxPairPasses], pq[kMaxPairPasses];
+#pragma unroll
+    for (int ps = 0; ps < kMaxPairPasses; ++ps) {
+        int idx = lane + 32 * ps;
+        int r = 1 + idx / max(w, 1), q = 1 + idx % max(w, 1);
+        bool ok = (idx < npairs) && (q <= r);
+        pr[ps] = ok ? r : 0;
+        pq[ps] = ok ? q : 0;
+    }
+    for (int j = 0; j < m; ++j) {
+        const double piv = Mb[j * W1];
+        const double inv = (piv > kPivotRel * diag0[j]) ? 1.0 / piv : 0.0;
+        const int rmax = min(w, m - 1 - j);
+        if (npairs <= 32 * kMaxPairPasses) {
+#pragma unroll
+            for (int ps = 0; ps < kMaxPairPasses; ++ps) {
+                const int r = pr[ps], q = pq[ps];
+                if (r != 0 && r <= rmax) {
+                    const double lr = Mb[(j + r) * W1 + r];
+                    const double lq = Mb[(j + q) * W1 + q];
+                    Mb[(j + r) * W1 + (r - q)] -= lr * lq * inv;
+                }
+            }
+        } else {
+            for (int idx = lane; idx < npairs; idx += 32) {
+                const int r = 1 + idx / w, q = 1 + idx % w;
+                if (q <= r && r <= rmax) {
+                    const double lr = Mb[(j + r) * W1 + r];
+                    const double lq = Mb[(j + q) * W1 + q];
+                    Mb[(j + r) * W1 + (r - q)] -= lr * lq * inv;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) Mb[j * W1] = inv;
+    }
+    __syncwarp();
+}
+
+// ---- solve M v = r in place with the factor produced by band_factor.  One warp.
+__device__ void band_solve(const double *Mb, double *v, int m, int w, int lane) {
+    const int W1 = w + 1;
+    // forward: L t = r     (column sweeps, lanes over the w sub-diagonal entries)
+    for (int j = 0; j < m; ++j) {
+        const double t = v[j] * Mb[j * W1];
+        for (int r = lane + 1; r <= w; r += 32)
+            if (j + r < m) v[j + r] -= Mb[(j + r) * W1 + r] * t;
+        __syncwarp();
+    }
+    // t' = D^-1 t
+    for (int j = lane; j < m; j += 32) v[j] *= Mb[j * W1];
+    __syncwarp();
+    // backward: L' v = t'
+    for (int i = m - 1; i > 0; --i) {
+        const double vi = v[i];
+        for (int r = lane + 1; r <= w; r += 32)
+            if (i - r >= 0) v[i - r] -= Mb[(i - r) * W1] * Mb[i * W1 + r] * vi;
+        __syncwarp();
+    }
+}
+
+struct Work {   // per-warp shared-memory vectors
+    double *x, *z, *c, *rd, *d, *dx, *cor;     // n
+    double *s, *wv, *u, *ru, *cors;            // nb
+    double *y, *b, *rp, *dy;                   // m
+    double *Mb;                                // m*(w+1)
+};
+
+// Newton direction for the complementarity targets  x z -> ax,  s w -> as  (ax = as = 0: affine predictor;
+// ax_j = smu - cor_j: centring corrector).  On exit W.dx = dx, W.dy = dy.
+template <bool CORR>
+__device__ __forceinline__ void newton(const Work &W, const Hot &H, const KParams &P, double smu, int lane) {
+    const int n = P.n, nb = P.nb, m = P.m;
+    for (int j = lane; j < n; j += 32) {
+        const double xj = W.x[j], zj = W.z[j];
+        double h = W.rd[j] + zj;
+        if (CORR) h -= (smu - W.cor[j]) / xj;
+        if (j < nb) {
+            const double sj = W.s[j], wj = W.wv[j];
+            double as = -wj * W.ru[j];
+            if (CORR) as += smu - W.cors[j];
+            h += as / sj - wj;
+        }
+        W.dx[j] = W.d[j] * h;
+    }
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) {
+        double acc = W.rp[i];
+        for (int q = H.A_ptr[i]; q < H.A_ptr[i + 1]; ++q) acc += H.A_val[q] * W.dx[H.A_idx[q]];
+        W.dy[i] = acc;
+    }
+    __syncwarp();
+    band_solve(W.Mb, W.dy, m, P.w, lane);
+    for (int j = lane; j < n; j += 32) {
+        double acc = 0.0;
+        for (int q = H.At_ptr[j]; q < H.At_ptr[j + 1]; ++q) acc += H.At_val[q] * W.dy[H.At_idx[q]];
+        W.dx[j] = W.d[j] * acc - W.dx[j];
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ double ratio(double v, double dv) { return dv < 0.0 ? -v / dv : 1e300; }
+
+__device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long long p, int lane) {
+    const int n = P.n, nb = P.nb, m = P.m, w = P.w;
+    const double *cp = P.cparams + p * (long long)P.Pc;
+    const double *rp_ = P.rparams + p * P.rstride;
+    // ---- instantiate c, b, u, objective constant from the parameter maps
+    double cmax = 0.0, bmax = 0.0, kconst = 0.0;
+    for (int j = lane; j < n; j += 32) {
+        double acc = P.c0[j];
+        for (int q = P.cm_ptr[j]; q < P.cm_ptr[j + 1]; ++q) acc += P.cm_val[q] * cp[P.cm_idx[q]];
+        W.c[j] = acc;
+        cmax = fmax(cmax, fabs(acc));
+    }
+    for (int i = lane; i < m; i += 32) {
+        double acc = P.b0[i];
+        for (int q = P.bm_ptr[i]; q < P.bm_ptr[i + 1]; ++q) acc += P.bm_val[q] * rp_[P.bm_idx[q]];
+        W.b[i] = acc;
+        bmax = fmax(bmax, fabs(acc));
+    }
+    for (int j = lane; j < nb; j += 32) {
+        double acc = P.u0[j];
+        for (int q = P.um_ptr[j]; q < P.um_ptr[j + 1]; ++q) acc += P.um_val[q] * rp_[P.um_idx[q]];
+        W.u[j] = acc;
+        bmax = fmax(bmax, acc);
+    }
+    for (int r = lane; r < P.Pr; r += 32) kconst += P.omap[r] * rp_[r];
+    for (int r = lane; r < P.Pc; r += 32) kconst += P.ocmap[r] * cp[r];
+    kconst = warp_sum(kconst) + P.o0;
+    cmax = warp_max(cmax);
+    bmax = warp_max(bmax);
+    const double beta_b = bmax > 0.0 ? bmax : 1.0;
+    const double beta_c = cmax > 0.0 ? cmax : 1.0;
+    // ---- scale, start point
+    double bsmax = 0.0;
+    for (int i = lane; i < m; i += 32) {
+        const double v = W.b[i] / beta_b;
+        W.b[i] = v;
+        W.y[i] = 0.0;
+        bsmax = fmax(bsmax, fabs(v));
+    }
+    for (int j = lane; j < n; j += 32) {
+        W.c[j] = W.c[j] / beta_c;
+        double xj = 1.0;
+        if (j < nb) {
+            const double uj = fmax(W.u[j] / beta_b, 1e-10);
+            W.u[j] = uj;
+            xj = fmin(1.0, 0.5 * uj);
+            W.s[j] = uj - xj;
+            W.wv[j] = 1.0;
+        }
+        W.x[j] = xj;
+        W.z[j] = 1.0;
+    }
+    bsmax = warp_max(bsmax);
+    const double nrm_b = 1.0 + bsmax, nrm_c = 1.0 + (cmax > 0.0 ? 1.0 : 0.0);
+    const double ntot = (double)(n + nb);
+    __syncwarp();
+
+    int status = DSP_MAX_ITER, it = 0;
+    double pobj = 0.0;
+    for (it = 0; it <= P.max_iter; ++it) {
+        // ---- residuals, complementarity, objectives
+        double pmax = 0.0, dmax = 0.0, musum = 0.0, po = 0.0, dobj = 0.0;
+        for (int i = lane; i < m; i += 32) {
+            double acc = W.b[i];
+            for (int q = H.A_ptr[i]; q < H.A_ptr[i + 1]; ++q) acc -= H.A_val[q] * W.x[H.A_idx[q]];
+            W.rp[i] = acc;
+            pmax = fmax(pmax, fabs(acc));
+            dobj += W.b[i] * W.y[i];
+        }
+        for (int j = lane; j < n; j += 32) {
+            const double xj = W.x[j], zj = W.z[j];
+            double acc = W.c[j] - zj;
+            for (int q = H.At_ptr[j]; q < H.At_ptr[j + 1]; ++q) acc -= H.At_val[q] * W.y[H.At_idx[q]];
+            double t = zj / xj;
+            if (j < nb) {
+                const double sj = W.s[j], wj = W.wv[j], uj = W.u[j];
+                acc += wj;
+                const double r = uj - xj - sj;
+                W.ru[j] = r;
+                pmax = fmax(pmax, fabs(r));
+                musum += sj * wj;
+                dobj -= uj * wj;
+                t += wj / sj;
+            }
+            W.rd[j] = acc;
+            W.d[j] = 1.0 / t;
+            dmax = fmax(dmax, fabs(acc));
+            musum += xj * zj;
+            po += W.c[j] * xj;
+        }
+        pmax = warp_max(pmax);
+        dmax = warp_max(dmax);
+        musum = warp_sum(musum);
+        po = warp_sum(po);
+        dobj = warp_sum(dobj);
+        pobj = po;
+        const double mu = musum / ntot;
+        const double gap = fabs(po - dobj) / fmax(kGapFloor, fabs(po));
+        if (!(mu == mu) || !(po == po) || mu > 1e100) { status = DSP_NUMERICAL; break; }
+        if (pmax / nrm_b < P.tol && dmax / nrm_c < P.tol && gap < P.tol) { status = DSP_OPTIMAL; break; }
+        if (it == P.max_iter) break;
+        __syncwarp();
+        // ---- assemble the band of M = A D A'
+        const int nent = m * (w + 1);
+        for (int e = lane; e < nent; e += 32) {
+            double acc = 0.0;
+            for (int q = H.asm_ptr[e]; q < H.asm_ptr[e + 1]; ++q) acc += H.asm_val[q] * W.d[H.asm_col[q]];
+            W.Mb[e] = acc;
+        }
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) W.dy[i] = W.Mb[i * (w + 1)];
+        __syncwarp();
+        band_factor(W.Mb, W.dy, m, w, lane);
+        // ---- affine predictor
+        newton<false>(W, H, P, 0.0, lane);
+        double ap = 1e300, ad = 1e300;
+        for (int j = lane; j < n; j += 32) {
+            const double xj = W.x[j], zj = W.z[j], dxj = W.dx[j];
+            const double dzj = -zj - zj * dxj / xj;
+            ap = fmin(ap, ratio(xj, dxj));
+            ad = fmin(ad, ratio(zj, dzj));
+            if (j < nb) {
+                const double sj = W.s[j], wj = W.wv[j];
+                const double dsj = W.ru[j] - dxj;
+                const double dwj = -wj - wj * dsj / sj;
+                ap = fmin(ap, ratio(sj, dsj));
+                ad = fmin(ad, ratio(wj, dwj));
+            }
+        }
+        ap = fmin(1.0, warp_min(ap));
+        ad = fmin(1.0, warp_min(ad));
+        double mua = 0.0;
+        for (int j = lane; j < n; j += 32) {
+            const double xj = W.x[j], zj = W.z[j], dxj = W.dx[j];
+            const double dzj = -zj - zj * dxj / xj;
+            mua += (xj + ap * dxj) * (zj + ad * dzj);
+            W.cor[j] = dxj * dzj;
+            if (j < nb) {
+                const double sj = W.s[j], wj = W.wv[j];
+                const double dsj = W.ru[j] - dxj;
+                const double dwj = -wj - wj * dsj / sj;
+                mua += (sj + ap * dsj) * (wj + ad * dwj);
+                W.cors[j] = dsj * dwj;
+            }
+        }
+        mua = warp_sum(mua) / ntot;
+        const double sg = mua / mu;
+        const double smu = sg * sg * sg * mu;
+        __syncwarp();
+        // ---- centring corrector
+        newton<true>(W, H, P, smu, lane);
+        ap = 1e300; ad = 1e300;
+        for (int j = lane; j < n; j += 32) {
+            const double xj = W.x[j], zj = W.z[j], dxj = W.dx[j];
+            const double dzj = (smu - W.cor[j]) / xj - zj - zj * dxj / xj;
+            ap = fmin(ap, ratio(xj, dxj));
+            ad = fmin(ad, ratio(zj, dzj));
+            if (j < nb) {
+                const double sj = W.s[j], wj = W.wv[j];
+                const double dsj = W.ru[j] - dxj;
+                const double dwj = (smu - W.cors[j]) / sj - wj - wj * dsj / sj;
+                ap = fmin(ap, ratio(sj, dsj));
+                ad = fmin(ad, ratio(wj, dwj));
+            }
+        }
+        ap = fmin(1.0, P.step_frac * warp_min(ap));
+        ad = fmin(1.0, P.step_frac * warp_min(ad));
+        for (int j = lane; j < n; j += 32) {
+            const double xj = W.x[j], zj = W.z[j], dxj = W.dx[j];
+            const double dzj = (smu - W.cor[j]) / xj - zj - zj * dxj / xj;
+            if (j < nb) {
+                const double sj = W.s[j], wj = W.wv[j];
+                const double dsj = W.ru[j] - dxj;
+                const double dwj = (smu - W.cors[j]) / sj - wj - wj * dsj / sj;
+                W.s[j] = sj + ap * dsj;
+                W.wv[j] = wj + ad * dwj;
+            }
+            W.x[j] = xj + ap * dxj;
+            W.z[j] = zj + ad * dzj;
+        }
+        for (int i = lane; i < m; i += 32) W.y[i] += ad * W.dy[i];
+        __syncwarp();
+    }
+    // ---- results
+    if (lane == 0) {
+        P.obj[p] = pobj * beta_b * beta_c + kconst;
+        P.status[p] = status;
+        P.iters[p] = it;
+    }
+    if (P.x_out) {
+        double *xo = P.x_out + p * (long long)n;
+        for (int j = lane; j < n; j += 32) xo[j] = W.x[j] * beta_b;
+    }
+    if (P.y_out) {
+        double *yo = P.y_out + p * (long long)m;
+        for (int i = lane; i < m; i += 32) yo[i] = W.y[i] * beta_c;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) dsp_ipm_band_kernel(const KParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned char *hot = P.hot_g;
+    if (P.hot_in_smem) {
+        tma_stage(smem + 16, P.hot_g, P.hot_bytes, (uint64_t *)smem);
+        hot = smem + 16;
+    }
+    const Hot H = hot_views(hot, P);
+    double *base = (double *)(smem + P.prob_off) + (size_t)warp * P.prob_doubles;
+    Work W;
+    const int n = P.n, nb = P.nb, m = P.m;
+    W.x = base; W.z = W.x + n; W.c = W.z + n; W.rd = W.c + n; W.d = W.rd + n; W.dx = W.d + n; W.cor = W.dx + n;
+    W.s = W.cor + n; W.wv = W.s + nb; W.u = W.wv + nb; W.ru = W.u + nb; W.cors = W.ru + nb;
+    W.y = W.cors + nb; W.b = W.y + m; W.rp = W.b + m; W.dy = W.rp + m;
+    W.Mb = W.dy + m;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(P.ticket, 1ULL);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((long long)t >= P.N) break;
+        solve_one(W, H, P, (long long)t, lane);
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+thread_local std::string g_err;
+std::mutex g_mu;
+int64_t g_launches = 0;
+int g_last_grid = 0, g_last_block = 0, g_last_smem = 0, g_last_ppc = 0;
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+            return DSP_E_CUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+template <class T>
+int upload(const std::vector<T> &h, T **d) {
+    *d = nullptr;
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    CK(cudaMalloc((void **)d, bytes));
+    if (!h.empty()) CK(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+}  // namespace
+
+struct dsp_template {
+    KParams kp;
+    int device;
+    int sm_count;
+    int smem_optin;
+    std::vector<void *> dev_allocs;
+    unsigned long long *ticket;
+    // host-call staging (pinned) and device buffers, grown on demand
+    int64_t cap_N;
+    double *h_cp, *h_rp, *h_obj, *h_x, *h_y;
+    int32_t *h_status, *h_iters;
+    double *d_cp, *d_rp, *d_obj, *d_x, *d_y;
+    int32_t *d_status, *d_iters;
+    bool cap_x, cap_y;
+    int64_t cap_rp_rows;
+    cudaStream_t stream;
+};
+
+extern "C" {
+
+const char *dsp_lp_version(void) { return DSP_VERSION; }
+const char *dsp_lp_last_error(void) { return g_err.c_str(); }
+int64_t dsp_lp_launch_count(void) { return g_launches; }
+int dsp_lp_last_launch(int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *ppc) {
+    if (grid) *grid = g_last_grid;
+    if (block) *block = g_last_block;
+    if (smem_bytes) *smem_bytes = g_last_smem;
+    if (ppc) *ppc = g_last_ppc;
+    return 0;
+}
+
+void dsp_lp_default_opts(dsp_opts *o) {
+    o->tol = 1e-8;
+    o->max_iter = 60;
+    o->step_frac = 0.9995;
+    o->device = -1;
+}
+
+int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
+    if (!D || !out || D->m <= 0 || D->n <= 0 || D->nb < 0 || D->nb > D->n || D->w < 0 || D->w >= D->m + 1) {
+        g_err = "dsp_lp_template_create: bad dimensions";
+        return DSP_E_ARG;
+    }
+    const int m = D->m, n = D->n, nb = D->nb, w = D->w;
+    const int nnz = D->A_ptr[m];
+    const int nent = m * (w + 1);
+    const int nasm = D->asm_ptr[nent];
+    // CSC of A
+    std::vector<int> At_ptr(n + 1, 0), At_idx(nnz);
+    std::vector<double> At_val(nnz);
+    for (int q = 0; q < nnz; ++q) {
+        if (D->A_idx[q] < 0 || D->A_idx[q] >= n) { g_err = "A_idx out of range"; return DSP_E_ARG; }
+        At_ptr[D->A_idx[q] + 1]++;
+    }
+    for (int j = 0; j < n; ++j) At_ptr[j + 1] += At_ptr[j];
+    {
+        std::vector<int> fill(At_ptr.begin(), At_ptr.end() - 1);
+        for (int i = 0; i < m; ++i)
+            for (int q = D->A_ptr[i]; q < D->A_ptr[i + 1]; ++q) {
+                int dst = fill[D->A_idx[q]]++;
+                At_idx[dst] = i;
+                At_val[dst] = D->A_val[q];
+            }
+    }
+    // hot blob
+    size_t dbl = (size_t)nnz * 2 + nasm;
+    size_t ints = (size_t)(m + 1) + nnz + (n + 1) + nnz + (nent + 1) + nasm;
+    size_t hot_bytes = dbl * 8 + ints * 4;
+    hot_bytes = (hot_bytes + 15) / 16 * 16;
+    std::vector<unsigned char> hot(hot_bytes, 0);
+    {
+        double *pd = (double *)hot.data();
+        memcpy(pd, D->A_val, (size_t)nnz * 8); pd += nnz;
+        memcpy(pd, At_val.data(), (size_t)nnz * 8); pd += nnz;
+        memcpy(pd, D->asm_val, (size_t)nasm * 8); pd += nasm;
+        int *pi = (int *)pd;
+        memcpy(pi, D->A_ptr, (size_t)(m + 1) * 4); pi += m + 1;
+        memcpy(pi, D->A_idx, (size_t)nnz * 4); pi += nnz;
+        memcpy(pi, At_ptr.data(), (size_t)(n + 1) * 4); pi += n + 1;
+        memcpy(pi, At_idx.data(), (size_t)nnz * 4); pi += nnz;
+        memcpy(pi, D->asm_ptr, (size_t)(nent + 1) * 4); pi += nent + 1;
+        memcpy(pi, D->asm_col, (size_t)nasm * 4);
+    }
+    dsp_template *T = new dsp_template();
+    memset(&T->kp, 0, sizeof(KParams));
+    T->cap_N = 0; T->cap_x = T->cap_y = false; T->cap_rp_rows = 0;
+    T->h_cp = T->h_rp = T->h_obj = T->h_x = T->h_y = nullptr; T->h_status = T->h_iters = nullptr;
+    T->d_cp = T->d_rp = T->d_obj = T->d_x = T->d_y = nullptr; T->d_status = T->d_iters = nullptr;
+    T->stream = nullptr;
+    CK(cudaGetDevice(&T->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, T->device));
+    T->sm_count = prop.multiProcessorCount;
+    T->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    KParams &K = T->kp;
+    K.m = m; K.n = n; K.nb = nb; K.w = w; K.Pc = D->Pc; K.Pr = D->Pr; K.nnz = nnz; K.nasm = nasm;
+    K.hot_bytes = (int)hot_bytes;
+    K.o0 = D->o0;
+    auto up_d = [&](const double *src, size_t cnt, const double **dst) -> int {
+        std::vector<double> v(src, src + cnt);
+        double *d;
+        int rc = upload(v, &d);
+        if (rc) return rc;
+        T->dev_allocs.push_back(d);
+        *dst = d;
+        return 0;
+    };
+    auto up_i = [&](const int32_t *src, size_t cnt, const int **dst) -> int {
+        std::vector<int> v(src, src + cnt);
+        int *d;
+        int rc = upload(v, &d);
+        if (rc) return rc;
+        T->dev_allocs.push_back(d);
+        *dst = d;
+        return 0;
+    };
+    {
+        unsigned char *d;
+        int rc = upload(hot, &d);
+        if (rc) return rc;
+        T->dev_allocs.push_back(d);
+        K.hot_g = d;
+    }
+    int rc = 0;
+    rc |= up_d(D->c0, n, &K.c0);
+    rc |= up_d(D->b0, m, &K.b0);
+    rc |= up_d(D->u0, nb, &K.u0);
+    rc |= up_d(D->omap, D->Pr, &K.omap);
+    rc |= up_d(D->ocmap, D->Pc, &K.ocmap);
+    rc |= up_i(D->cmap.ptr, n + 1, &K.cm_ptr);
+    rc |= up_i(D->cmap.idx, D->cmap.ptr[n], &K.cm_idx);
+    rc |= up_d(D->cmap.val, D->cmap.ptr[n], &K.cm_val);
+    rc |= up_i(D->bmap.ptr, m + 1, &K.bm_ptr);
+    rc |= up_i(D->bmap.idx, D->bmap.ptr[m], &K.bm_idx);
+    rc |= up_d(D->bmap.val, D->bmap.ptr[m], &K.bm_val);
+    rc |= up_i(D->umap.ptr, nb + 1, &K.um_ptr);
+    rc |= up_i(D->umap.idx, D->umap.ptr[nb], &K.um_idx);
+    rc |= up_d(D->umap.val, D->umap.ptr[nb], &K.um_val);
+    if (rc) return DSP_E_CUDA;
+    CK(cudaMalloc((void **)&T->ticket, sizeof(unsigned long long)));
+    T->dev_allocs.push_back(T->ticket);
+    K.prob_doubles = 7 * n + 5 * nb + 4 * m + m * (w + 1);
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaStreamCreateWithFlags(&T->stream, cudaStreamNonBlocking));
+    *out = T;
+    return 0;
+}
+
+void dsp_lp_template_destroy(dsp_template *T) {
+    if (!T) return;
+    for (void *p : T->dev_allocs) cudaFree(p);
+    cudaFree(T->d_cp); cudaFree(T->d_rp); cudaFree(T->d_obj); cudaFree(T->d_x); cudaFree(T->d_y);
+    cudaFree(T->d_status); cudaFree(T->d_iters);
+    cudaFreeHost(T->h_cp); cudaFreeHost(T->h_rp); cudaFreeHost(T->h_obj); cudaFreeHost(T->h_x); cudaFreeHost(T->h_y);
+    cudaFreeHost(T->h_status); cudaFreeHost(T->h_iters);
+    if (T->stream) cudaStreamDestroy(T->stream);
+    delete T;
+}
+
+int dsp_lp_solve_batch(const dsp_template *T, int64_t N, const double *cparams, const double *rparams,
+                       int64_t rparams_stride, const dsp_opts *opts, double *obj, int32_t *status, int32_t *iters,
+                       double *x, double *y, void *cuda_stream) {
+    if (!T || N < 0 || !obj || !status || !iters || (T->kp.Pc > 0 && !cparams) || (T->kp.Pr > 0 && !rparams)) {
+        g_err = "dsp_lp_solve_batch: bad arguments";
+        return DSP_E_ARG;
+    }
+    if (N == 0) return 0;
+    dsp_opts o;
+    dsp_lp_default_opts(&o);
+    if (opts) o = *opts;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    KParams K = T->kp;
+    K.N = N; K.cparams = cparams; K.rparams = rparams; K.rstride = rparams_stride;
+    K.tol = o.tol; K.step_frac = o.step_frac; K.max_iter = o.max_iter;
+    K.obj = obj; K.status = status; K.iters = iters; K.x_out = x; K.y_out = y;
+    K.ticket = T->ticket;
+    // geometry: one persistent CTA per SM; as many warps (= LPs in flight) as shared memory allows
+    const size_t prob_bytes = (size_t)K.prob_doubles * 8;
+    const size_t budget = (size_t)T->smem_optin;
+    int hot_in_smem = 1;
+    size_t off = 16 + (size_t)K.hot_bytes;
+    long long warps = budget > off ? (long long)((budget - off) / prob_bytes) : 0;
+    if (warps < 4) {   // template too large to stage: read it through L2
+        hot_in_smem = 0;
+        off = 16;
+        warps = (long long)((budget - off) / prob_bytes);
+    }
+    if (warps < 1) {
+        g_err = "dsp_lp_solve_batch: one LP does not fit in shared memory (" + std::to_string(prob_bytes) + " bytes)";
+        return DSP_E_SMEM;
+    }
+    warps = std::min<long long>(warps, kMaxWarps);
+    long long ctas = std::min<long long>(T->sm_count, (N + warps - 1) / warps);
+    // spread a small batch over all SMs
+    if (ctas < T->sm_count && N > ctas) {
+        ctas = std::min<long long>(T->sm_count, N);
+        warps = std::min<long long>(warps, (N + ctas - 1) / ctas);
+    }
+    K.hot_in_smem = hot_in_smem;
+    K.prob_off = (int)off;
+    const size_t smem = off + (size_t)warps * prob_bytes;
+    CK(cudaMemsetAsync(T->ticket, 0, sizeof(unsigned long long), st));
+    dsp_ipm_band_kernel<<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+    CK(cudaGetLastError());
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_launches++;
+        g_last_grid = (int)ctas; g_last_block = (int)(warps * 32); g_last_smem = (int)smem; g_last_ppc = (int)warps;
+    }
+    return 0;
+}
+
+static int ensure_capacity(dsp_template *T, int64_t N, int64_t rp_rows, bool want_x, bool want_y) {
+    const KParams &K = T->kp;
+    if (N > T->cap_N || rp_rows > T->cap_rp_rows || (want_x && !T->cap_x) || (want_y && !T->cap_y)) {
+        int64_t cap = std::max<int64_t>(N, T->cap_N);
+        int64_t rcap = std::max<int64_t>(rp_rows, T->cap_rp_rows);
+        bool cx = want_x || T->cap_x, cy = want_y || T->cap_y;
+        cudaFree(T->d_cp); cudaFree(T->d_rp); cudaFree(T->d_obj); cudaFree(T->d_x); cudaFree(T->d_y);
+        cudaFree(T->d_status); cudaFree(T->d_iters);
+        cudaFreeHost(T->h_cp); cudaFreeHost(T->h_rp); cudaFreeHost(T->h_obj); cudaFreeHost(T->h_x); cudaFreeHost(T->h_y);
+        cudaFreeHost(T->h_status); cudaFreeHost(T->h_iters);
+        T->d_x = T->d_y = T->h_x = T->h_y = nullptr;
+        size_t ncp = (size_t)std::max<int64_t>(1, cap * K.Pc), nrp = (size_t)std::max<int64_t>(1, rcap * K.Pr);
+        CK(cudaMalloc((void **)&T->d_cp, ncp * 8)); CK(cudaMallocHost((void **)&T->h_cp, ncp * 8));
+        CK(cudaMalloc((void **)&T->d_rp, nrp * 8)); CK(cudaMallocHost((void **)&T->h_rp, nrp * 8));
+        CK(cudaMalloc((void **)&T->d_obj, cap * 8)); CK(cudaMallocHost((void **)&T->h_obj, cap * 8));
+        CK(cudaMalloc((void **)&T->d_status, cap * 4)); CK(cudaMallocHost((void **)&T->h_status, cap * 4));
+        CK(cudaMalloc((void **)&T->d_iters, cap * 4)); CK(cudaMallocHost((void **)&T->h_iters, cap * 4));
+        if (cx) { CK(cudaMalloc((void **)&T->d_x, (size_t)cap * K.n * 8)); CK(cudaMallocHost((void **)&T->h_x, (size_t)cap * K.n * 8)); }
+        if (cy) { CK(cudaMalloc((void **)&T->d_y, (size_t)cap * K.m * 8)); CK(cudaMallocHost((void **)&T->h_y, (size_t)cap * K.m * 8)); }
+        T->cap_N = cap; T->cap_rp_rows = rcap; T->cap_x = cx; T->cap_y = cy;
+    }
+    return 0;
+}
+
+int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, const double *rparams,
+                            int64_t rparams_stride, const dsp_opts *opts, double *obj, int32_t *status,
+                            int32_t *iters, double *x, double *y) {
+    if (!T || N < 0) { g_err = "dsp_lp_solve_batch_host: bad arguments"; return DSP_E_ARG; }
+    if (N == 0) return 0;
+    const KParams &K = T->kp;
+    const int64_t rp_rows = (rparams_stride == 0) ? 1 : N;
+    int rc = ensure_capacity(T, N, rp_rows, x != nullptr, y != nullptr);
+    if (rc) return rc;
+    cudaStream_t st = T->stream;
+    if (K.Pc > 0) {
+        memcpy(T->h_cp, cparams, (size_t)N * K.Pc * 8);
+        CK(cudaMemcpyAsync(T->d_cp, T->h_cp, (size_t)N * K.Pc * 8, cudaMemcpyHostToDevice, st));
+    }
+    int64_t dstride = 0;
+    if (K.Pr > 0) {
+        if (rparams_stride != 0 && rparams_stride != K.Pr) {   // compact strided rows
+            for (int64_t r = 0; r < rp_rows; ++r) memcpy(T->h_rp + r * K.Pr, rparams + r * rparams_stride, (size_t)K.Pr * 8);
+        } else {
+            memcpy(T->h_rp, rparams, (size_t)rp_rows * K.Pr * 8);
+        }
+        CK(cudaMemcpyAsync(T->d_rp, T->h_rp, (size_t)rp_rows * K.Pr * 8, cudaMemcpyHostToDevice, st));
+        dstride = (rparams_stride == 0) ? 0 : K.Pr;
+    }
+    rc = dsp_lp_solve_batch(T, N, T->d_cp, T->d_rp, dstride, opts, T->d_obj, T->d_status, T->d_iters,
+                            x ? T->d_x : nullptr, y ? T->d_y : nullptr, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(T->h_obj, T->d_obj, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(T->h_status, T->d_status, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(T->h_iters, T->d_iters, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    if (x) CK(cudaMemcpyAsync(T->h_x, T->d_x, (size_t)N * K.n * 8, cudaMemcpyDeviceToHost, st));
+    if (y) CK(cudaMemcpyAsync(T->h_y, T->d_y, (size_t)N * K.m * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(obj, T->h_obj, (size_t)N * 8);
+    memcpy(status, T->h_status, (size_t)N * 4);
+    memcpy(iters, T->h_iters, (size_t)N * 4);
+    if (x) memcpy(x, T->h_x, (size_t)N * K.n * 8);
+    if (y) memcpy(y, T->h_y, (size_t)N * K.m * 8);
+    return 0;
+}
+
+}  // extern "C"

@@ -88,7 +88,7 @@ class LPTemplate:
         return c, b, u, self.o0 + float(self.omap @ rparams) + float(self.ocmap @ cparams)
 
     # ------------------------------------------------------------------
-    def finalize(self, equilibrate=True):
+    def finalize(self, equilibrate=False):
         """Column order (bounded first), row order (min bandwidth of A A'), band assembly list."""
         A = self.A.tocsr()
         m, n = A.shape
@@ -229,7 +229,7 @@ class TemplateBuilder:
         for k, v in am.items():
             self.omap[k] += v
 
-    def build(self, equilibrate=True) -> LPTemplate:
+    def build(self, equilibrate=False) -> LPTemplate:
         # substitute x = lb + x' (and drop constant columns)
         lbs = np.array(self.lbs)
         for r, row in enumerate(self.arows):

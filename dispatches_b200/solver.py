@@ -1,0 +1,207 @@
+"""Python binding of the C-ABI (include/dsp_lp.h) -- ctypes over libdsp_lp.so.
+
+``BatchLPSolver(template)`` is the batched replacement of the reference's per-LP
+``pyo.SolverFactory("cbc").solve(m)`` (wind_battery_LMP.py:266-267): the template is uploaded once, then
+``solve`` (device tensors in / device tensors out, stream ordered) or ``solve_host`` (numpy in / numpy out,
+copies included) handles a whole scenario batch.  torch is used only for device memory and streams.
+
+There is NO CPU fallback: if the CUDA library is missing or no GPU is visible the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from pathlib import Path
+
+import numpy as np
+
+from .lp_template import LPTemplate
+
+_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libdsp_lp.so"
+_lib = None
+
+OPTIMAL, MAX_ITER, NUMERICAL = 0, 1, 2
+STATUS_NAMES = {OPTIMAL: "optimal", MAX_ITER: "maxIterations", NUMERICAL: "error"}
+
+EXPORTS = ["dsp_lp_template_create", "dsp_lp_template_destroy", "dsp_lp_default_opts", "dsp_lp_solve_batch",
+           "dsp_lp_solve_batch_host", "dsp_lp_launch_count", "dsp_lp_last_launch", "dsp_lp_last_error",
+           "dsp_lp_version"]
+
+
+class _ParamMap(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("idx", C.c_void_p), ("val", C.c_void_p)]
+
+
+class _Desc(C.Structure):
+    _fields_ = [("m", C.c_int32), ("n", C.c_int32), ("nb", C.c_int32), ("w", C.c_int32),
+                ("Pc", C.c_int32), ("Pr", C.c_int32),
+                ("A_ptr", C.c_void_p), ("A_idx", C.c_void_p), ("A_val", C.c_void_p),
+                ("asm_ptr", C.c_void_p), ("asm_col", C.c_void_p), ("asm_val", C.c_void_p),
+                ("c0", C.c_void_p), ("cmap", _ParamMap),
+                ("b0", C.c_void_p), ("bmap", _ParamMap),
+                ("u0", C.c_void_p), ("umap", _ParamMap),
+                ("o0", C.c_double), ("omap", C.c_void_p), ("ocmap", C.c_void_p)]
+
+
+class _Opts(C.Structure):
+    _fields_ = [("tol", C.c_double), ("max_iter", C.c_int32), ("step_frac", C.c_double), ("device", C.c_int32)]
+
+
+def load_library():
+    """Loads libdsp_lp.so; raises loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(f"{_LIB_PATH} is missing: build it with `python -m dispatches_b200.csrc.build` "
+                           "(the solver has no CPU fallback)")
+    lib = C.CDLL(str(_LIB_PATH))
+    lib.dsp_lp_template_create.argtypes = [C.POINTER(_Desc), C.POINTER(C.c_void_p)]
+    lib.dsp_lp_template_create.restype = C.c_int
+    lib.dsp_lp_template_destroy.argtypes = [C.c_void_p]
+    lib.dsp_lp_template_destroy.restype = None
+    lib.dsp_lp_default_opts.argtypes = [C.POINTER(_Opts)]
+    lib.dsp_lp_default_opts.restype = None
+    lib.dsp_lp_solve_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Opts),
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dsp_lp_solve_batch.restype = C.c_int
+    lib.dsp_lp_solve_batch_host.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Opts),
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dsp_lp_solve_batch_host.restype = C.c_int
+    lib.dsp_lp_launch_count.restype = C.c_int64
+    lib.dsp_lp_last_launch.argtypes = [C.POINTER(C.c_int32)] * 4
+    lib.dsp_lp_last_launch.restype = C.c_int
+    lib.dsp_lp_last_error.restype = C.c_char_p
+    lib.dsp_lp_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def launch_count() -> int:
+    return int(load_library().dsp_lp_launch_count())
+
+
+def last_launch():
+    g, b, s, p = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    load_library().dsp_lp_last_launch(C.byref(g), C.byref(b), C.byref(s), C.byref(p))
+    return dict(grid=g.value, block=b.value, smem_bytes=s.value, problems_per_cta=p.value)
+
+
+@dataclasses.dataclass
+class LPResult:
+    obj: object          # [N] objective incl. constant (the reference's Objective value, e.g. -NPV*1e-5)
+    status: object       # [N] OPTIMAL / MAX_ITER / NUMERICAL
+    iters: object        # [N]
+    x: object = None     # [N,n] template-space primal (see LPTemplate.col_names / to_model_space)
+    y: object = None     # [N,m] row duals
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class BatchLPSolver:
+    def __init__(self, template: LPTemplate, tol=1e-8, max_iter=60, step_frac=0.9995):
+        self.lib = load_library()
+        self.t = template
+        t = template
+        nb = t.nb
+        A = t.A.tocsr(); A.sort_indices()
+        Cm = t.Cmap.tocsr(); Bm = t.Bmap.tocsr(); Um = t.Umap.tocsr()[:nb]
+        keep = dict(A_ptr=_i32(A.indptr), A_idx=_i32(A.indices), A_val=_f64(A.data),
+                    asm_ptr=_i32(t.asm_ptr), asm_col=_i32(t.asm_col), asm_val=_f64(t.asm_val),
+                    c0=_f64(t.c0), b0=_f64(t.b0), u0=_f64(t.u0[:nb]),
+                    cm_ptr=_i32(Cm.indptr), cm_idx=_i32(Cm.indices), cm_val=_f64(Cm.data),
+                    bm_ptr=_i32(Bm.indptr), bm_idx=_i32(Bm.indices), bm_val=_f64(Bm.data),
+                    um_ptr=_i32(Um.indptr), um_idx=_i32(Um.indices), um_val=_f64(Um.data),
+                    omap=_f64(t.omap if t.Pr else np.zeros(1)), ocmap=_f64(t.ocmap if t.Pc else np.zeros(1)))
+        p = lambda k: keep[k].ctypes.data_as(C.c_void_p)
+        d = _Desc(m=t.m, n=t.n, nb=nb, w=t.w, Pc=t.Pc, Pr=t.Pr,
+                  A_ptr=p("A_ptr"), A_idx=p("A_idx"), A_val=p("A_val"),
+                  asm_ptr=p("asm_ptr"), asm_col=p("asm_col"), asm_val=p("asm_val"),
+                  c0=p("c0"), cmap=_ParamMap(p("cm_ptr"), p("cm_idx"), p("cm_val")),
+                  b0=p("b0"), bmap=_ParamMap(p("bm_ptr"), p("bm_idx"), p("bm_val")),
+                  u0=p("u0"), umap=_ParamMap(p("um_ptr"), p("um_idx"), p("um_val")),
+                  o0=float(t.o0), omap=p("omap"), ocmap=p("ocmap"))
+        h = C.c_void_p()
+        rc = self.lib.dsp_lp_template_create(C.byref(d), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"dsp_lp_template_create failed ({rc}): {self.lib.dsp_lp_last_error().decode()}")
+        self.handle = h
+        self.opts = _Opts()
+        self.lib.dsp_lp_default_opts(C.byref(self.opts))
+        self.opts.tol, self.opts.max_iter, self.opts.step_frac = tol, max_iter, step_frac
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.dsp_lp_template_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.dsp_lp_last_error().decode()}")
+
+    # ------------------------------------------------------------------ device tensors
+    def solve(self, cparams, rparams=None, want_x=False, want_y=False, out=None):
+        """cparams: cuda float64 [N,Pc]; rparams: cuda float64 [N,Pr] or [Pr] (shared by the batch).
+        Stream-ordered on torch's current stream, no synchronisation."""
+        import torch
+        t = self.t
+        if not cparams.is_cuda or cparams.dtype != torch.float64:
+            raise ValueError("cparams must be a CUDA float64 tensor (no CPU path)")
+        cparams = cparams.contiguous()
+        N = cparams.shape[0]
+        dev = cparams.device
+        rstride = 0
+        rptr = None
+        if t.Pr:
+            rparams = rparams.contiguous()
+            rstride = 0 if rparams.dim() == 1 else t.Pr
+            rptr = rparams.data_ptr()
+        if out is None:
+            out = LPResult(torch.empty(N, dtype=torch.float64, device=dev),
+                           torch.empty(N, dtype=torch.int32, device=dev),
+                           torch.empty(N, dtype=torch.int32, device=dev),
+                           torch.empty((N, t.n), dtype=torch.float64, device=dev) if want_x else None,
+                           torch.empty((N, t.m), dtype=torch.float64, device=dev) if want_y else None)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = self.lib.dsp_lp_solve_batch(self.handle, N, cparams.data_ptr(), rptr, rstride, C.byref(self.opts),
+                                         out.obj.data_ptr(), out.status.data_ptr(), out.iters.data_ptr(),
+                                         out.x.data_ptr() if out.x is not None else None,
+                                         out.y.data_ptr() if out.y is not None else None, C.c_void_p(stream))
+        self._check(rc, "dsp_lp_solve_batch")
+        return out
+
+    # ------------------------------------------------------------------ host arrays (copies included)
+    def solve_host(self, cparams, rparams=None, want_x=False, want_y=False):
+        t = self.t
+        cparams = _f64(np.atleast_2d(cparams))
+        N = cparams.shape[0]
+        rstride, rptr = 0, None
+        if t.Pr:
+            rparams = _f64(rparams)
+            rstride = 0 if rparams.ndim == 1 else t.Pr
+            rptr = rparams.ctypes.data_as(C.c_void_p)
+        obj = np.empty(N); status = np.empty(N, np.int32); iters = np.empty(N, np.int32)
+        x = np.empty((N, t.n)) if want_x else None
+        y = np.empty((N, t.m)) if want_y else None
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        rc = self.lib.dsp_lp_solve_batch_host(self.handle, N, vp(cparams), rptr, rstride, C.byref(self.opts),
+                                              vp(obj), vp(status), vp(iters), vp(x), vp(y))
+        self._check(rc, "dsp_lp_solve_batch_host")
+        return LPResult(obj, status, iters, x, y)
+
+    # ------------------------------------------------------------------
+    def to_model_space(self, x):
+        """template-space primal -> the reference model's Var values (lower-bound shift, column scaling)."""
+        return x * self.t.col_scale + self.t.col_shift

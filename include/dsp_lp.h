@@ -1,0 +1,104 @@
+/*
+ * dsp_lp.h -- C ABI of the B200 batched dispatch-LP solver (libdsp_lp.so).
+ *
+ * The reference (gmlc-dispatches/dispatches) is pure Python and has no FFI; the boundary this library
+ * sits behind is Pyomo's solver-plugin call
+ *
+ *     opt = pyo.SolverFactory("cbc");  opt.solve(m)        wind_battery_LMP.py:266-267
+ *     opt = pyo.SolverFactory('cbc');  opt.solve(m)        wind_battery_PEM_LMP.py:296-298
+ *     solver = SolverFactory("gurobi"); solver.solve(m)    nuclear_case/report/price_taker_analysis.py:365,403
+ *     SolverFactory('ipopt').solve(m, tee=True)            fossil_case/.../pricetaker_with_multiperiod_integrated_storage_usc.py:126,137
+ *
+ * invoked once per (design point, LMP signal) by the sweep loops
+ * (run_pricetaker_wind_battery.py:37-70, run_pricetaker_wind_PEM.py:100-110, price_taker_analysis.py:372-403).
+ * Those calls write an LP file, fork a solver process and parse a .sol file per LP.  Here the shared
+ * constraint structure is handed over ONCE (dsp_lp_template_create) and the whole scenario batch is solved
+ * by one kernel launch (dsp_lp_solve_batch).  Each entry point below names the reference interface it
+ * replaces; INTEGRATION.md shows the ctypes / Pyomo-plugin binding.
+ *
+ * Problem class (one template = one flowsheet x horizon x design mode):
+ *
+ *     min c'x + k   s.t.  A x = b,  0 <= x <= u         A: m x n, CSR, shared by the batch
+ *     c = c0 + Cmap*cparams   b = b0 + Bmap*rparams   u = u0 + Umap*rparams   k = o0 + omap.rparams + ocmap.cparams
+ *
+ * Columns 0..nb-1 are the upper-bounded ones.  Rows must be ordered so that A*A' is banded with half
+ * bandwidth w (multi-period flowsheets are block tridiagonal in time); asm_* is the assembly list of the
+ * lower band of M = A*diag(d)*A':  M[i][i-k] = sum_{p in asm_ptr[i*(w+1)+k] ..} asm_val[p]*d[asm_col[p]].
+ * dispatches_b200/lp_template.py computes all of it.
+ *
+ * All pointers in dsp_lp_solve_batch are DEVICE pointers, the call is stream-ordered and does not
+ * synchronise.  dsp_lp_solve_batch_host takes HOST pointers and does the copies itself.
+ * Return value: 0 on success, a negative DSP_E_* code on argument / launch errors.  Per-problem outcome
+ * is reported only through status[] (DSP_OPTIMAL, ...), like SolverResults.solver.termination_condition.
+ */
+#ifndef DSP_LP_H
+#define DSP_LP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dsp_template dsp_template;   /* opaque, owns device copies of the template */
+
+/* sparse affine map in CSR: row r touches params idx[ptr[r]..ptr[r+1]) with coefficients val[..] */
+typedef struct {
+    const int32_t *ptr;
+    const int32_t *idx;
+    const double  *val;
+} dsp_param_map;
+
+typedef struct {
+    int32_t m, n, nb, w;          /* rows, columns, bounded columns (first nb), half bandwidth of A A' */
+    int32_t Pc, Pr;               /* lengths of cparams / rparams */
+    const int32_t *A_ptr, *A_idx;  const double *A_val;        /* CSR, m rows                         */
+    const int32_t *asm_ptr, *asm_col; const double *asm_val;   /* band assembly list, m*(w+1) entries  */
+    const double *c0;  dsp_param_map cmap;                     /* n rows  over cparams                 */
+    const double *b0;  dsp_param_map bmap;                     /* m rows  over rparams                 */
+    const double *u0;  dsp_param_map umap;                     /* nb rows over rparams                 */
+    double o0; const double *omap /*[Pr]*/; const double *ocmap /*[Pc]*/;
+} dsp_template_desc;
+
+typedef struct {
+    double  tol;          /* relative residual / gap tolerance (default 1e-8)           */
+    int32_t max_iter;     /* default 60                                                  */
+    double  step_frac;    /* fraction of the step to the boundary (default 0.9995)       */
+    int32_t device;       /* CUDA device ordinal, -1 = current                           */
+} dsp_opts;
+
+enum { DSP_OPTIMAL = 0, DSP_MAX_ITER = 1, DSP_NUMERICAL = 2 };
+enum { DSP_E_ARG = -1, DSP_E_CUDA = -2, DSP_E_SMEM = -3 };
+
+/* Replaces: the per-LP model hand-over inside SolverFactory(..).solve(m) (Pyomo LP/NL writer), done once. */
+int dsp_lp_template_create(const dsp_template_desc *desc, dsp_template **out);
+void dsp_lp_template_destroy(dsp_template *t);
+
+void dsp_lp_default_opts(dsp_opts *o);
+
+/* Replaces: the sweep loop of opt.solve(m) calls (one per scenario).  Device pointers, stream-ordered.
+ *   cparams [N,Pc], rparams [N,Pr] (or [1,Pr] broadcast when rparams_stride == 0)
+ *   obj [N]  objective c'x + k ; status [N] ; iters [N] ; x [N,n] or NULL ; y [N,m] or NULL          */
+int dsp_lp_solve_batch(const dsp_template *t, int64_t N,
+                       const double *cparams, const double *rparams, int64_t rparams_stride,
+                       const dsp_opts *opts,
+                       double *obj, int32_t *status, int32_t *iters, double *x, double *y,
+                       void *cuda_stream);
+
+/* Same with HOST pointers: pinned staging, H2D of the parameters, kernel, D2H of the results, one sync.
+ * This is the call the Pyomo plugin / sweep drivers make; bench.py's "e2e" number times it.          */
+int dsp_lp_solve_batch_host(dsp_template *t, int64_t N,
+                            const double *cparams, const double *rparams, int64_t rparams_stride,
+                            const dsp_opts *opts,
+                            double *obj, int32_t *status, int32_t *iters, double *x, double *y);
+
+/* Introspection used by tests / bench: kernel launches issued so far, last launch geometry. */
+int64_t dsp_lp_launch_count(void);
+int dsp_lp_last_launch(int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *problems_per_cta);
+const char *dsp_lp_last_error(void);
+const char *dsp_lp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,74 @@
+"""Regenerates tests/golden/* from the reference's committed DATA files (run HERE, in the dev container;
+/root/reference does not exist on the GPU box, so the outputs are committed).
+
+    python tests/golden/make_golden.py
+
+Writes
+  ../../dispatches_b200/data/lmp_pool.npz -- real price/capacity-factor series the synthetic scenario batches are drawn from
+                           (SURVEY.md §8(d)): day windows of Wind_Thermal_Dispatch.csv DA/RT LMPs at buses
+                           122/303/309/317 (load_parameters.py:82-112), the 3100 cluster days of
+                           nuclear_case/lmp_signal.json, the 8736-h 303_DALMP / 303_WIND_1-DACF series,
+                           the fossil 24-h / 168-h LMP vectors are NOT copied (source literals).
+  wind_pem_golden.json  -- the reference's own committed result tables for the wind+PEM price-taker sweep
+                           (wind_PEM/wind_PEM_RT_1000.csv, design_wind_PEM_results.csv,
+                           design_wind_PEM_RT_results.csv: h2_price x pem_ratio -> annual_rev_h2, NPV) (the 8784-h parquet
+                           price / capacity-factor series they were computed on go into lmp_pool.npz as pq1000_* / pq500_*).
+  unit_kats.json        -- known answers of the reference's unit-model tests for the battery rows
+                           (unit_models/tests/test_battery.py:40-67, :95-119).
+No reference SOURCE is copied: only numeric data and test constants.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+
+REF = Path("/root/reference/dispatches")
+OUT = Path(__file__).parent
+
+
+def main():
+    rc = REF / "case_studies" / "renewables_case"
+    df = pd.read_csv(rc / "data" / "Wind_Thermal_Dispatch.csv")
+    assert len(df) == 8736
+    windows = []
+    for bus in ("122", "303", "309", "317"):
+        for mk in ("DA", "RT"):
+            windows.append(df[f"{bus}_{mk}LMP"].values.reshape(364, 24))
+    day_windows = np.concatenate(windows)                      # 2912 x 24
+    j = json.load(open(REF / "case_studies" / "nuclear_case" / "lmp_signal.json"))
+    cl = []
+    for sc in sorted(j, key=int):
+        for yr in sorted(j[sc], key=int):
+            for d in sorted(j[sc][yr], key=int):
+                cl.append([j[sc][yr][d][str(h)] for h in range(1, 25)])
+    cluster_days = np.array(cl, float)                         # 3100 x 24
+    assert cluster_days.shape == (3100, 24)
+    extra = {}
+    for shortfall in (1000, 500):
+        p = pd.read_parquet(rc / "data" / f"303_LMPs_15_reserve_{shortfall}_shortfall.parquet")
+        for col, key in (("LMP", "rt_lmp"), ("LMP DA", "da_lmp"), ("303_WIND_1-RTCF", "rt_cf"), ("303_WIND_1-DACF", "da_cf")):
+            extra[f"pq{shortfall}_{key}"] = p[col].values
+    np.savez_compressed(OUT.parent.parent / "dispatches_b200" / "data" / "lmp_pool.npz", day_windows=day_windows, cluster_days=cluster_days,
+                        dalmp_303=df["303_DALMP"].values, dacf_303=df["303_WIND_1-DACF"].values, **extra)
+
+    gold = {}
+    for name in ("wind_PEM_RT_1000", "design_wind_PEM_results", "design_wind_PEM_RT_results"):
+        t = pd.read_csv(rc / "wind_PEM" / f"{name}.csv")
+        keep = ["wind_mw", "batt_mw", "pem_mw", "h2_price_per_kg", "annual_rev_h2", "annual_rev_E", "NPV"]
+        gold[name] = t[[k for k in keep if k in t.columns]].to_dict(orient="list")
+    json.dump(gold, open(OUT / "wind_pem_golden.json", "w"))
+
+    kats = {
+        # test_battery.py:40-67: elec_in = 5 kW for dt = 1 h from empty -> SoC 4.75 kWh, throughput 2.5 kWh
+        "battery_charge": dict(elec_in=5.0, elec_out=0.0, soc0=0.0, thr0=0.0, soc=4.75, throughput=2.5),
+        # test_battery.py:95-119: soc0 = 5, thr0 = 5, elec_out fixed 5, state_of_charge fixed 0
+        #   -> the reference asserts energy_throughput == approx(7.638, rel=1e-3)
+        "battery_discharge": dict(soc0=5.0, thr0=5.0, elec_out=5.0, soc=0.0, throughput=7.638, rel=1e-3),
+    }
+    json.dump(kats, open(OUT / "unit_kats.json", "w"), indent=1)
+    print("wrote", [p.name for p in OUT.iterdir()])
+
+
+if __name__ == "__main__":
+    main()
