@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference's price-taker entry points, batched over LMP scenarios.
+
+Same names and argument meaning as the reference functions; the only extension is that ``DA_LMPs`` may be a
+2-D array [N, >=T] (one row per price scenario) and sizes may be arrays [N] (one entry per design point):
+
+  wind_battery_optimize(n_time_points, input_params, verbose)     wind_battery_LMP.py:172-269
+  wind_battery_pem_optimize(time_points, input_params, verbose)    wind_battery_PEM_LMP.py:180-298
+  record_results(res)                                              wind_battery_LMP.py:272-325
+  nuclear_dispatch_optimize(n_time_points, lmps, ...)              nuclear_flowsheet_multiperiod_class.py:72-155
+
+Where the reference builds a Pyomo MultiPeriodModel and calls SolverFactory("cbc").solve(m) once per signal,
+these build (and cache) one LPTemplate per (flowsheet, T) and hand the whole batch to the CUDA solver.
+``design_opt`` other than False is not on the GPU path yet (dense border in the KKT system).
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+
+from . import templates as TP
+from .solver import BatchLPSolver, OPTIMAL, STATUS_NAMES
+
+_SOLVERS = {}
+
+
+def get_solver(kind, T, **kw) -> BatchLPSolver:
+    key = (kind, T, tuple(sorted(kw.items())))
+    if key not in _SOLVERS:
+        builder = dict(wind_battery=TP.wind_battery, wind_battery_pem=TP.wind_battery_pem, nuclear=TP.nuclear,
+                       fossil_surrogate=TP.fossil_surrogate)[kind]
+        _SOLVERS[key] = BatchLPSolver(builder(T, **kw))
+    return _SOLVERS[key]
+
+
+def _capacity_factors(input_params, T):
+    wr = input_params["wind_resource"]
+    if isinstance(wr, dict):       # the reference's {t: {'wind_resource_config': {'capacity_factor': [cf]}}}
+        return np.array([wr[t]["wind_resource_config"]["capacity_factor"][0] for t in range(T)], float)
+    wr = np.asarray(wr, float)
+    return wr[..., :T]
+
+
+@dataclasses.dataclass
+class PriceTakerResult:
+    kind: str
+    T: int
+    lmp: np.ndarray                 # [N,T] $/MWh
+    obj: np.ndarray                 # [N]   the reference Objective value (-NPV*1e-5 for the renewables cases)
+    status: np.ndarray
+    iters: np.ndarray
+    x: np.ndarray | None            # [N,n] model-space values of the template columns
+    col_names: list
+    sizes: dict
+
+    @property
+    def NPV(self):
+        return -self.obj * 1e5
+
+    @property
+    def termination_condition(self):
+        return [STATUS_NAMES[int(s)] for s in self.status]
+
+    def var(self, name, t=None):
+        """Values [N] of a reference Var, e.g. var("battery.state_of_charge[0]", t=3)."""
+        full = name if t is None else f"blk[{t}].fs.{name}"
+        if full in self.col_names:
+            return self.x[:, self.col_names.index(full)]
+        if self.kind.startswith("wind_battery") and full == f"blk[{self.T - 1}].fs.battery.state_of_charge[0]":
+            return np.zeros(self.x.shape[0])       # presolved constant (periodic constraint)
+        raise KeyError(full)
+
+    def series(self, name):
+        """[N,T] time series of a per-period Var."""
+        return np.stack([self.var(name, t) for t in range(self.T)], axis=1)
+
+    # quantities the reference exposes as model Expressions (wind_battery_LMP.py:252-263)
+    @property
+    def annual_elec_revenue(self):
+        ann = 52.0 / (self.T / 168.0)
+        out = self.series("splitter.grid_elec[0]")
+        try:
+            out = out + self.series("battery.elec_out[0]")
+        except KeyError:
+            pass
+        return (self.lmp * 1e-3 * out).sum(1) * ann
+
+    @property
+    def annual_revenue(self):
+        ann = 52.0 / (self.T / 168.0)
+        fixed = self.sizes["wind_kw"] * TP.WIND_OP_COST / 8760.0 + self.sizes["batt_kw"] * TP.BATT_OP_COST / 8760.0
+        rev = self.annual_elec_revenue
+        if "pem_kw" in self.sizes:
+            fixed = fixed + self.sizes["pem_kw"] * TP.PEM_OP_COST / 8760.0
+            rev = rev + self.annual_rev_h2
+        return rev - fixed * self.T * ann
+
+    @property
+    def annual_rev_h2(self):
+        ann = 52.0 / (self.T / 168.0)
+        pe = self.series("pem.electricity[0]")
+        return pe.sum(1) * TP.PEM_ELEC_TO_MOL / TP.H2_MOLS_PER_KG * 3600.0 * self.sizes["h2_price"] * ann
+
+
+def _lmps(input_params, T):
+    lmp = np.asarray(input_params["DA_LMPs"], float)
+    lmp = np.atleast_2d(lmp)[:, :T]
+    if lmp.shape[1] != T:
+        raise ValueError(f"DA_LMPs must provide {T} values per scenario")
+    return np.ascontiguousarray(lmp)
+
+
+def wind_battery_optimize(n_time_points, input_params, verbose=False, want_solution=True):
+    if input_params.get("design_opt", False):
+        raise NotImplementedError("design_opt=True is not on the batched GPU path (fixed-design sweeps only)")
+    T = int(n_time_points)
+    lmp = _lmps(input_params, T)
+    cf = _capacity_factors(input_params, T)
+    sol = get_solver("wind_battery", T, extant_wind=bool(input_params.get("extant_wind", True)))
+    rp = TP.wind_battery_rparams(T, cf, input_params["wind_mw"], input_params["batt_mw"])
+    if rp.shape[0] == 1:
+        rp = rp[0]
+    elif rp.shape[0] != lmp.shape[0]:
+        raise ValueError("sizes / capacity factors must be scalar or match the number of LMP scenarios")
+    r = sol.solve_host(lmp, rp, want_x=want_solution)
+    if verbose:
+        print(f"b200ipm: {lmp.shape[0]} LPs, iterations mean {r.iters.mean():.1f} max {r.iters.max()}, "
+              f"non-optimal {(r.status != OPTIMAL).sum()}")
+    N = lmp.shape[0]
+    sizes = dict(wind_kw=np.broadcast_to(np.asarray(input_params["wind_mw"], float) * 1e3, (N,)),
+                 batt_kw=np.broadcast_to(np.asarray(input_params["batt_mw"], float) * 1e3, (N,)))
+    return PriceTakerResult("wind_battery", T, lmp, r.obj, r.status, r.iters,
+                            sol.to_model_space(r.x) if want_solution else None, sol.t.col_names, sizes)
+
+
+def wind_battery_pem_optimize(time_points, input_params, verbose=False, want_solution=True):
+    if input_params.get("design_opt", False):
+        raise NotImplementedError("design_opt != False is not on the batched GPU path (fixed-design sweeps only)")
+    T = int(time_points)
+    lmp = _lmps(input_params, T)
+    N = lmp.shape[0]
+    cf = _capacity_factors(input_params, T)
+    batt = np.asarray(input_params["batt_mw"], float)
+    with_batt = bool(np.any(batt > 0))
+    sol = get_solver("wind_battery_pem", T, with_battery=with_batt, extant_wind=bool(input_params.get("extant_wind", True)))
+    rp = TP.wind_battery_rparams(T, cf, input_params["wind_mw"], batt, pem_mw=input_params["pem_mw"])
+    rp = rp[0] if rp.shape[0] == 1 else rp
+    h2 = np.broadcast_to(np.asarray(input_params["h2_price_per_kg"], float), (N,))
+    cp = np.ascontiguousarray(np.concatenate([lmp, h2[:, None]], axis=1))
+    r = sol.solve_host(cp, rp, want_x=want_solution)
+    sizes = dict(wind_kw=np.broadcast_to(np.asarray(input_params["wind_mw"], float) * 1e3, (N,)),
+                 batt_kw=np.broadcast_to(batt * 1e3, (N,)),
+                 pem_kw=np.broadcast_to(np.asarray(input_params["pem_mw"], float) * 1e3, (N,)), h2_price=h2)
+    return PriceTakerResult("wind_battery_pem", T, lmp, r.obj, r.status, r.iters,
+                            sol.to_model_space(r.x) if want_solution else None, sol.t.col_names, sizes)
+
+
+def nuclear_dispatch_optimize(n_time_points, lmps, want_solution=False, **flowsheet_options):
+    T = int(n_time_points)
+    lmp = np.ascontiguousarray(np.atleast_2d(np.asarray(lmps, float))[:, :T])
+    sol = get_solver("nuclear", T, **flowsheet_options)
+    r = sol.solve_host(lmp, None, want_x=want_solution)
+    return PriceTakerResult("nuclear", T, lmp, r.obj, r.status, r.iters,
+                            sol.to_model_space(r.x) if want_solution else None, sol.t.col_names, {})
+
+
+def record_results(res: PriceTakerResult, k=0):
+    """The reference's record_results tuple (wind_battery_LMP.py:272-325) for scenario k."""
+    soc = res.series("battery.state_of_charge[0]")[k]
+    batt_to_grid = res.series("battery.elec_out[0]")[k] * 1e-3
+    wind_to_grid = res.series("splitter.grid_elec[0]")[k] * 1e-3
+    wind_to_batt = res.series("battery.elec_in[0]")[k] * 1e-3
+    wind_gen = wind_to_grid + wind_to_batt
+    lmp = res.lmp[k]
+    fixed = res.sizes["wind_kw"][k] * TP.WIND_OP_COST / 8760.0 + res.sizes["batt_kw"][k] * TP.BATT_OP_COST / 8760.0
+    elec_revenue = lmp * 1e-3 * (wind_to_grid + batt_to_grid) * 1e3 - fixed
+    return (list(soc), list(wind_gen), list(batt_to_grid), list(wind_to_grid), list(wind_to_batt), list(elec_revenue),
+            list(lmp), res.sizes["wind_kw"][k] * 1e-3, res.sizes["batt_kw"][k] * 1e-3,
+            float(res.annual_revenue[k]), float(res.NPV[k]))

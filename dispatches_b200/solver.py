@@ -44,7 +44,7 @@ class _Desc(C.Structure):
 
 
 class _Opts(C.Structure):
-    _fields_ = [("tol", C.c_double), ("max_iter", C.c_int32), ("step_frac", C.c_double), ("device", C.c_int32)]
+    _fields_ = [("tol", C.c_double), ("feas_tol", C.c_double), ("max_iter", C.c_int32), ("step_frac", C.c_double), ("device", C.c_int32)]
 
 
 def load_library():
@@ -105,7 +105,7 @@ def _f64(a):
 
 
 class BatchLPSolver:
-    def __init__(self, template: LPTemplate, tol=1e-8, max_iter=60, step_frac=0.9995):
+    def __init__(self, template: LPTemplate, tol=1e-9, feas_tol=1e-9, max_iter=60, step_frac=0.9995):
         self.lib = load_library()
         self.t = template
         t = template
@@ -134,7 +134,7 @@ class BatchLPSolver:
         self.handle = h
         self.opts = _Opts()
         self.lib.dsp_lp_default_opts(C.byref(self.opts))
-        self.opts.tol, self.opts.max_iter, self.opts.step_frac = tol, max_iter, step_frac
+        self.opts.tol, self.opts.feas_tol, self.opts.max_iter, self.opts.step_frac = tol, feas_tol, max_iter, step_frac
 
     def close(self):
         if getattr(self, "handle", None):

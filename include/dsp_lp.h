@@ -61,7 +61,8 @@ typedef struct {
 } dsp_template_desc;
 
 typedef struct {
-    double  tol;          /* relative residual / gap tolerance (default 1e-8)           */
+    double  tol;          /* relative duality-gap tolerance (default 1e-9)              */
+    double  feas_tol;     /* relative primal / dual residual tolerance (default 1e-9)   */
     int32_t max_iter;     /* default 60                                                  */
     double  step_frac;    /* fraction of the step to the boundary (default 0.9995)       */
     int32_t device;       /* CUDA device ordinal, -1 = current                           */

@@ -43,8 +43,11 @@ def _init_worker(kind, kwargs):
 
 def _build(kind, lmp, extra, kwargs):
     if kind == "wind_battery":
-        cf, wind_mw, batt_mw = extra
-        return lp_models.wind_battery_raw(lmp, cf, wind_mw, batt_mw, **kwargs)
+        if extra is not None:           # per-LP design point / capacity factors (design sweeps)
+            cf, wind_mw, batt_mw = extra
+            kw = {k: v for k, v in kwargs.items() if k not in ("cf", "wind_mw", "batt_mw")}
+            return lp_models.wind_battery_raw(lmp, cf, wind_mw, batt_mw, **kw)
+        return lp_models.wind_battery_raw(lmp, **kwargs)
     if kind == "nuclear":
         return lp_models.nuclear_raw(lmp, **kwargs)
     if kind == "fossil_surrogate":

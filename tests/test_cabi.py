@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports every entry point include/dsp_lp.h declares (no compute, no GPU)."""
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_functions():
+    h = (ROOT / "include" / "dsp_lp.h").read_text()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(dsp_lp_\w+)\s*\(", h)))
+
+
+def test_header_declares_the_boundary():
+    f = declared_functions()
+    for name in ("dsp_lp_template_create", "dsp_lp_solve_batch", "dsp_lp_solve_batch_host", "dsp_lp_template_destroy"):
+        assert name in f
+
+
+def test_library_exports_every_declared_symbol(cuda_solver_lib):
+    from dispatches_b200 import solver
+    for name in declared_functions():
+        assert hasattr(cuda_solver_lib, name), name
+    assert sorted(solver.EXPORTS) == declared_functions()
+    assert b"sm_100a" in cuda_solver_lib.dsp_lp_version()
+
+
+def test_sass_is_sm100a_with_tma_staging():
+    """The built library carries sm_100a SASS with the TMA bulk copy (UBLKCP) and FP64 FMAs."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        import pytest
+        pytest.skip("cuobjdump not on PATH")
+    from dispatches_b200.csrc import build
+    lib = build.build()
+    sass = subprocess.run(["cuobjdump", "-sass", str(lib)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass and "UBLKCP" in sass and "DFMA" in sass
+
+
+def test_no_cpu_fallback_in_product():
+    """The product package never imports the oracle and the solver refuses non-CUDA tensors."""
+    for p in (ROOT / "dispatches_b200").rglob("*.py"):
+        src = p.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, p
+    import numpy as np
+    import pytest
+    import torch
+    from dispatches_b200 import solver, templates as TP
+    if torch.cuda.is_available():
+        pytest.skip("checks the no-GPU failure mode")
+    with pytest.raises(RuntimeError):
+        solver.BatchLPSolver(TP.nuclear(4)).solve_host(np.zeros((1, 4)))

@@ -1,0 +1,41 @@
+"""The interior-point ALGORITHM (numpy mirror of the CUDA kernel, oracle/ipm_numpy.py) against HiGHS on the
+hard price signals: exact zeros, 10 000 $/MWh spikes."""
+import numpy as np
+import pytest
+from scipy.optimize import linprog
+
+from dispatches_b200 import scenarios as SC
+from dispatches_b200 import templates as TP
+from oracle import ipm_numpy as I
+
+TOL_OBJ = 1e-6      # north_star: objective within 1e-6 relative
+
+
+def _batch(t, cps, rp):
+    cs, bs, us, ks = zip(*(t.instantiate(cp, rp) for cp in cps))
+    return np.array(cs), np.array(bs), np.array(us), np.array(ks)
+
+
+def test_mirror_wind_battery_200():
+    t = TP.wind_battery(24)
+    lmp, cf, W, P = SC.c2(200)
+    rp = TP.wind_battery_rparams(24, cf, W, P)[0]
+    c, b, u, k = _batch(t, lmp, rp)
+    r = I.solve_batch(t.A.toarray(), b, c, u, tol=1e-8, eta=0.9995)
+    assert (r["status"] == I.OPTIMAL).all() and r["iters"].max() <= 30
+    ref = np.array([linprog(c[i], A_eq=t.A, b_eq=b[i], bounds=[(0, None if not np.isfinite(v) else v) for v in u[i]],
+                            method="highs-ds").fun for i in range(len(c))])
+    err = np.abs(r["obj"] - ref) / np.maximum(1.0, np.abs(ref + k))
+    assert err.max() < TOL_OBJ
+    assert (np.abs(r["obj"] - ref) / np.maximum(1e-3, np.abs(ref))).max() < 1e-6   # LP part alone
+
+
+def test_mirror_nuclear_50():
+    t = TP.nuclear(48)
+    lmp = SC.c3(50)
+    c, b, u, k = _batch(t, lmp, np.zeros(0))
+    r = I.solve_batch(t.A.toarray(), b, c, u, tol=1e-8, eta=0.9995)
+    assert (r["status"] == I.OPTIMAL).all()
+    ref = np.array([linprog(c[i], A_eq=t.A, b_eq=b[i], bounds=[(0, None if not np.isfinite(v) else v) for v in u[i]],
+                            method="highs-ds").fun for i in range(len(c))])
+    assert (np.abs(r["obj"] - ref) / np.maximum(1.0, np.abs(ref + k))).max() < TOL_OBJ

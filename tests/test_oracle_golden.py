@@ -1,0 +1,88 @@
+"""The oracle (oracle/lp_models.py + HiGHS) against the reference's own committed results and unit-test
+known answers -- this is what pins the restatement."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from dispatches_b200 import scenarios as SC
+from oracle import highs as H
+from oracle import lp_models as L
+
+GOLD = Path(__file__).parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return json.load(open(GOLD / "wind_pem_golden.json"))
+
+
+@pytest.mark.parametrize("table,lmp_key,cf_key,rows", [
+    # reference tables: run_pricetaker_wind_PEM.py:100-110 with market "RT" / "DA" on the 1000-$ shortfall parquet
+    ("wind_PEM_RT_1000", "pq1000_rt_lmp", "pq1000_rt_cf", (1, 4, 8)),
+])
+def test_wind_pem_full_year_rows(gold, table, lmp_key, cf_key, rows):
+    """8784-period wind+PEM LP (batt_mw = 0, PEM size fixed) reproduces the committed NPV / H2 revenue."""
+    p = SC.pool()
+    tab = gold[table]
+    for r in rows:
+        assert tab["pem_mw"][r] > 0          # pem_mw == 0 rows differ by 2e-4 in the reference itself
+        lp = L.wind_battery_raw(p[lmp_key], p[cf_key], tab["wind_mw"][r], 0.0, pem_mw=tab["pem_mw"][r],
+                                h2_price=tab["h2_price_per_kg"][r])
+        obj, x = H.solve(lp)
+        rep = L.wind_battery_report(lp, x, p[lmp_key])
+        assert rep["NPV"] == pytest.approx(tab["NPV"][r], rel=2e-7)
+        assert rep["annual_rev_h2"] == pytest.approx(tab["annual_rev_h2"][r], rel=2e-7)
+        assert -obj * 1e5 == pytest.approx(rep["NPV"], rel=1e-12)
+
+
+def test_wind_pem_optimised_pem_size(gold):
+    """design_opt="PEM" row (pem_ratio None in run_pricetaker_wind_PEM.py:36-37): optimal PEM size 64.7 MW."""
+    p = SC.pool()
+    tab = gold["wind_PEM_RT_1000"]
+    r = 5
+    lp = L.wind_battery_raw(p["pq1000_rt_lmp"], p["pq1000_rt_cf"], tab["wind_mw"][r], 0.0, pem_mw=355.0,
+                            h2_price=tab["h2_price_per_kg"][r], design_opt="PEM")
+    obj, x = H.solve(lp)
+    assert x[lp.meta["Pc"]] * 1e-3 == pytest.approx(tab["pem_mw"][r], rel=2e-3)
+    assert -obj * 1e5 == pytest.approx(tab["NPV"][r], rel=1e-6)
+
+
+def test_battery_unit_known_answers():
+    """unit_models/tests/test_battery.py:40-67 and :95-119 through the raw one-period rows."""
+    k = json.load(open(GOLD / "unit_kats.json"))
+    a = k["battery_charge"]
+    soc = a["soc0"] + L.ETA_C * a["elec_in"] - a["elec_out"] / L.ETA_D
+    thr = a["thr0"] + 0.5 * (a["elec_in"] + a["elec_out"])
+    assert soc == pytest.approx(a["soc"], abs=1e-12) and thr == pytest.approx(a["throughput"], abs=1e-12)
+    # same rows inside the LP: a 1-period wind+battery model with everything pinned by bounds
+    lp = L.wind_battery_raw([10.0], [1.0], wind_mw=0.005, batt_mw=0.005)
+    v = lp.meta["v"]
+    lp.lb[v["i", 0]] = lp.ub[v["i", 0]] = 5.0
+    lp.lb[v["o", 0]] = lp.ub[v["o", 0]] = 0.0
+    # the periodic row forces s[T-1] = s0[0] = 0 in the 1-period model: drop it to look at the battery rows alone
+    keep = [i for i in range(lp.A_eq.shape[0]) if not (lp.A_eq[i, v["s", 0]] == 1.0 and lp.A_eq[i, v["s0", 0]] == -1.0
+                                                       and lp.A_eq[i].nnz == 2)]
+    lp.A_eq = lp.A_eq[keep]; lp.b_eq = lp.b_eq[keep]
+    _, x = H.solve(lp)
+    assert x[v["s", 0]] == pytest.approx(4.75, abs=1e-9)
+    assert x[v["e", 0]] == pytest.approx(2.5, abs=1e-9)
+    b = k["battery_discharge"]
+    i_needed = (b["elec_out"] / L.ETA_D - b["soc0"]) / L.ETA_C
+    thr = b["thr0"] + 0.5 * (i_needed + b["elec_out"])
+    assert thr == pytest.approx(b["throughput"], rel=b["rel"])
+
+
+def test_lmp_swap_matches_rebuild():
+    lmp, cf, W, P = SC.c2(3)
+    base = L.wind_battery_raw(lmp[0], cf, W, P)
+    c1 = L.swap_lmp(base, lmp[0], lmp[1])
+    assert np.allclose(c1, L.wind_battery_raw(lmp[1], cf, W, P).c, rtol=0, atol=1e-15)
+
+
+def test_batch_baseline_loop():
+    lmp, cf, W, P = SC.c2(6)
+    obj, dt, procs = H.solve_batch("wind_battery", lmp, kwargs=dict(cf=cf, wind_mw=W, batt_mw=P), procs=2)
+    ref = [H.solve(L.wind_battery_raw(l, cf, W, P))[0] for l in lmp]
+    assert np.allclose(obj, ref, rtol=1e-12)

@@ -1,0 +1,103 @@
+"""Host logic: the product's reduced templates (dispatches_b200/templates.py) against the raw oracle LPs."""
+import numpy as np
+import pytest
+from scipy.optimize import linprog
+
+from dispatches_b200 import scenarios as SC
+from dispatches_b200 import templates as TP
+from oracle import highs as H
+from oracle import lp_models as L
+
+
+def solve_template(t, cp, rp):
+    c, b, u, k = t.instantiate(cp, rp)
+    r = linprog(c, A_eq=t.A, b_eq=b, bounds=[(0, None if not np.isfinite(v) else v) for v in u], method="highs-ds")
+    assert r.status == 0, r.message
+    return r.fun + k, r.x
+
+
+@pytest.fixture(scope="module")
+def wb24():
+    return TP.wind_battery(24)
+
+
+def test_wind_battery_structure(wb24):
+    t = wb24
+    assert (t.m, t.n, t.nb) == (96, 167, 48)          # 4 rows/period; 5 cols + 2 slacks per period - s[T-1]
+    assert t.w == 4                                   # block tridiagonal in time -> half bandwidth 4
+    assert np.all(np.isfinite(t.u0[: t.nb])) and np.all(~np.isfinite(t.u0[t.nb:]))
+    # the assembly list reproduces A D A' for a random D
+    d = np.random.default_rng(0).uniform(0.1, 2.0, t.n)
+    M = (t.A @ np.diag(d) @ t.A.T)
+    M = np.asarray(M)
+    for i in range(t.m):
+        for k in range(t.w + 1):
+            e = i * (t.w + 1) + k
+            val = sum(t.asm_val[q] * d[t.asm_col[q]] for q in range(t.asm_ptr[e], t.asm_ptr[e + 1]))
+            ref = M[i, i - k] if i - k >= 0 else 0.0
+            assert val == pytest.approx(ref, abs=1e-12)
+    # nothing outside the band
+    ii, jj = np.nonzero(M)
+    assert np.max(np.abs(ii - jj)) <= t.w
+
+
+def test_wind_battery_matches_raw_oracle(wb24):
+    lmp, cf, W, P = SC.c2(8)
+    rp = TP.wind_battery_rparams(24, cf, W, P)[0]
+    for k in range(8):
+        a, _ = solve_template(wb24, lmp[k], rp)
+        b, _ = H.solve(L.wind_battery_raw(lmp[k], cf, W, P))
+        assert a == pytest.approx(b, rel=1e-11, abs=1e-9)
+
+
+def test_wind_battery_c1_and_design_points(wb24):
+    lmp, cf, W, P = SC.c1()
+    for (w_mw, p_mw) in ((W, P), (200.0, 10.0), (1600.0, 1600.0)):
+        rp = TP.wind_battery_rparams(24, cf, w_mw, p_mw)[0]
+        a, _ = solve_template(wb24, lmp, rp)
+        b, _ = H.solve(L.wind_battery_raw(lmp, cf, w_mw, p_mw))
+        assert a == pytest.approx(b, rel=1e-11, abs=1e-9)
+
+
+@pytest.mark.parametrize("with_battery", [True, False])
+def test_wind_battery_pem_matches_raw_oracle(with_battery):
+    t = TP.wind_battery_pem(24, with_battery=with_battery)
+    lmp, cf, W, P = SC.c2(4)
+    batt = 100.0 if with_battery else 0.0
+    rp = TP.wind_battery_rparams(24, cf, W, batt, pem_mw=200.0)[0]
+    for k in range(4):
+        a, _ = solve_template(t, np.append(lmp[k], 2.5), rp)
+        b, _ = H.solve(L.wind_battery_raw(lmp[k], cf, W, batt, pem_mw=200.0, h2_price=2.5))
+        assert a == pytest.approx(b, rel=1e-11, abs=1e-9)
+
+
+def test_nuclear_matches_raw_oracle():
+    t = TP.nuclear(48)
+    assert t.w == 1 and t.m == 48
+    lmp = SC.c3(4)
+    for k in range(4):
+        a, _ = solve_template(t, lmp[k], np.zeros(0))
+        b, _ = H.solve(L.nuclear_raw(lmp[k]))
+        assert a == pytest.approx(b, rel=1e-11, abs=1e-9)
+
+
+def test_fossil_surrogate_matches_raw_oracle():
+    t = TP.fossil_surrogate(168)
+    assert t.w <= 5
+    lmp = SC.c4(2)
+    for k in range(2):
+        a, x = solve_template(t, lmp[k], np.zeros(0))
+        b, _ = H.solve(L.fossil_surrogate_raw(lmp[k]))
+        assert a == pytest.approx(b, rel=1e-11, abs=1e-9)
+        xm = x * t.col_scale + t.col_shift
+        j = t.col_names.index("blk[3].fs.plant_power_out[0]")
+        assert 283.0 <= xm[j] <= 436.0 + 1e-9
+
+
+def test_scenarios_are_seeded_and_keep_hard_cases():
+    a, *_ = SC.c2(2000)
+    b, *_ = SC.c2(2000)
+    assert np.array_equal(a, b) and a.shape == (2000, 24)
+    assert (a == 0).mean() > 0.05 and a.max() > 5000.0      # exact zeros and scarcity spikes survive
+    lmp, cf, w, p = SC.c5(2, 2, 48)
+    assert lmp.shape == (2 * 2 * 48, 24) and cf.shape == lmp.shape and w.shape == (192,)
