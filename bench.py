@@ -46,7 +46,7 @@ def config(n_gpus):
     return {"workload": f"C2: renewables wind+battery 24-period price-taker, {BATCH} synthetic LMP scenarios per GPU "
                         f"(seed 20240101+rank), fixed design 847 MW wind / 211.75 MW 4-h battery",
             "T": T, "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "parallelism": f"scenario-shard x{n_gpus}",
-            "l2": "flushed between timed steps (256 MiB write)", "template": "wind_battery_T24 (m=96, n=167, w=4)"}
+            "l2": "flushed between timed steps (256 MiB write)", "template": "wind_battery_T24 (m=96, n=167, w=4)", "kernel": "dsp_ipm_stage_wb_kernel (warp per LP, lane per period, registers only)"}
 
 
 class ClockSampler:

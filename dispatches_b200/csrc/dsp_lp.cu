@@ -49,7 +49,7 @@ struct KParams {
     long long N;
     const double *cparams, *rparams;
     long long rstride;
-    double tol, feas_tol, step_frac;
+    double tol, feas_tol, step_frac, reg;
     int max_iter;
     double *obj, *x_out, *y_out;
     int *status, *iters;
@@ -321,7 +321,7 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
                 t += wj / sj;
             }
             W.rd[j] = acc;
-            W.d[j] = 1.0 / t;
+            W.d[j] = 1.0 / (t + P.reg);
             dmax = fmax(dmax, fabs(acc));
             musum += xj * zj;
             po += W.c[j] * xj;
@@ -470,6 +470,31 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) dsp_ipm_band_kernel(const K
     }
 }
 
+}  // namespace
+
+namespace {
+#include "dsp_stage_wb.cuh"
+
+// stage kernel: one warp per LP, one lane per period, all state in registers (see dsp_stage_wb.cuh)
+__global__ void __launch_bounds__(128) dsp_ipm_stage_wb_kernel(const KParams P, const stagewb::StageParams S) {
+    const int lane = threadIdx.x & 31;
+    stagewb::Out O;
+    O.obj = P.obj; O.x_out = P.x_out; O.y_out = P.y_out; O.status = P.status; O.iters = P.iters; O.n = P.n; O.m = P.m;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(P.ticket, 1ULL);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((long long)t >= P.N) break;
+        const double *cp = P.cparams + (long long)t * P.Pc;
+        const double *rp = P.rparams + (long long)t * P.rstride;
+        double kconst = 0.0;
+        for (int r = lane; r < P.Pr; r += 32) kconst += P.omap[r] * rp[r];
+        for (int r = lane; r < P.Pc; r += 32) kconst += P.ocmap[r] * cp[r];
+        kconst = stagewb::wsum(kconst) + P.o0;
+        stagewb::solve_one(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, P.step_frac, P.reg, P.max_iter, O, lane);
+    }
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -500,6 +525,9 @@ int upload(const std::vector<T> &h, T **d) {
 
 struct dsp_template {
     KParams kp;
+    bool has_stage;
+    stagewb::StageParams sp;
+    int stage_blocks_per_sm;
     int device;
     int sm_count;
     int smem_optin;
@@ -535,6 +563,8 @@ void dsp_lp_default_opts(dsp_opts *o) {
     o->max_iter = 60;
     o->step_frac = 0.9995;
     o->device = -1;
+    o->reg_primal = 1e-8;
+    o->kernel = DSP_KERNEL_AUTO;
 }
 
 int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
@@ -585,6 +615,7 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     dsp_template *T = new dsp_template();
     memset(&T->kp, 0, sizeof(KParams));
     T->cap_N = 0; T->cap_x = T->cap_y = false; T->cap_rp_rows = 0;
+    T->has_stage = false; T->stage_blocks_per_sm = 0;
     T->h_cp = T->h_rp = T->h_obj = T->h_x = T->h_y = nullptr; T->h_status = T->h_iters = nullptr;
     T->d_cp = T->d_rp = T->d_obj = T->d_x = T->d_y = nullptr; T->d_status = T->d_iters = nullptr;
     T->stream = nullptr;
@@ -647,6 +678,30 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     return 0;
 }
 
+int dsp_lp_template_set_stage_wb(dsp_template *T, const dsp_stage_wb_desc *d) {
+    if (!T || !d || d->T < 1 || d->T > 32) { g_err = "dsp_lp_template_set_stage_wb: need 1 <= T <= 32"; return DSP_E_ARG; }
+    if (T->kp.Pc < d->T || T->kp.Pr <= std::max(d->wcf_off + d->T - 1, d->p_off)) {
+        g_err = "dsp_lp_template_set_stage_wb: parameter layout does not fit the template";
+        return DSP_E_ARG;
+    }
+    stagewb::StageParams &S = T->sp;
+    S.T = d->T; S.a = d->a; S.binv = d->binv; S.hf = d->half; S.dl = d->delta; S.dur = d->dur; S.krev = d->k_rev;
+    S.wcf_off = d->wcf_off; S.p_off = d->p_off;
+    std::vector<int> ci(d->col_idx, d->col_idx + 7 * d->T), ri(d->row_idx, d->row_idx + 4 * d->T);
+    for (int v : ci) if (v < -1 || v >= T->kp.n) { g_err = "col_idx out of range"; return DSP_E_ARG; }
+    for (int v : ri) if (v < 0 || v >= T->kp.m) { g_err = "row_idx out of range"; return DSP_E_ARG; }
+    int *dci, *dri;
+    int rc = upload(ci, &dci); if (rc) return rc;
+    rc = upload(ri, &dri); if (rc) return rc;
+    T->dev_allocs.push_back(dci); T->dev_allocs.push_back(dri);
+    S.col_idx = dci; S.row_idx = dri;
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dsp_ipm_stage_wb_kernel, 128, 0));
+    T->stage_blocks_per_sm = std::max(nb, 1);
+    T->has_stage = true;
+    return 0;
+}
+
 void dsp_lp_template_destroy(dsp_template *T) {
     if (!T) return;
     for (void *p : T->dev_allocs) cudaFree(p);
@@ -672,9 +727,25 @@ int dsp_lp_solve_batch(const dsp_template *T, int64_t N, const double *cparams, 
     cudaStream_t st = (cudaStream_t)cuda_stream;
     KParams K = T->kp;
     K.N = N; K.cparams = cparams; K.rparams = rparams; K.rstride = rparams_stride;
-    K.tol = o.tol; K.feas_tol = o.feas_tol; K.step_frac = o.step_frac; K.max_iter = o.max_iter;
+    K.tol = o.tol; K.feas_tol = o.feas_tol; K.step_frac = o.step_frac; K.reg = o.reg_primal; K.max_iter = o.max_iter;
     K.obj = obj; K.status = status; K.iters = iters; K.x_out = x; K.y_out = y;
     K.ticket = T->ticket;
+    if (T->has_stage && o.kernel != DSP_KERNEL_BAND) {
+        // stage kernel: no shared memory; persistent warps, one LP per warp at a time
+        const int wpb = 4;
+        long long blocks = std::min<long long>((long long)T->sm_count * T->stage_blocks_per_sm, (N + wpb - 1) / wpb);
+        CK(cudaMemsetAsync(T->ticket, 0, sizeof(unsigned long long), st));
+        dsp_ipm_stage_wb_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(K, T->sp);
+        CK(cudaGetLastError());
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_launches++;
+        g_last_grid = (int)blocks; g_last_block = wpb * 32; g_last_smem = 0; g_last_ppc = wpb;
+        return 0;
+    }
+    if (o.kernel == DSP_KERNEL_STAGE) {
+        g_err = "dsp_lp_solve_batch: the template has no stage descriptor";
+        return DSP_E_ARG;
+    }
     // geometry: one persistent CTA per SM; as many warps (= LPs in flight) as shared memory allows
     const size_t prob_bytes = (size_t)K.prob_doubles * 8;
     const size_t budget = (size_t)T->smem_optin;

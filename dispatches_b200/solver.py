@@ -23,7 +23,9 @@ _lib = None
 OPTIMAL, MAX_ITER, NUMERICAL = 0, 1, 2
 STATUS_NAMES = {OPTIMAL: "optimal", MAX_ITER: "maxIterations", NUMERICAL: "error"}
 
-EXPORTS = ["dsp_lp_template_create", "dsp_lp_template_destroy", "dsp_lp_default_opts", "dsp_lp_solve_batch",
+KERNEL_AUTO, KERNEL_BAND, KERNEL_STAGE = 0, 1, 2
+
+EXPORTS = ["dsp_lp_template_create", "dsp_lp_template_destroy", "dsp_lp_template_set_stage_wb", "dsp_lp_default_opts", "dsp_lp_solve_batch",
            "dsp_lp_solve_batch_host", "dsp_lp_launch_count", "dsp_lp_last_launch", "dsp_lp_last_error",
            "dsp_lp_version"]
 
@@ -44,7 +46,14 @@ class _Desc(C.Structure):
 
 
 class _Opts(C.Structure):
-    _fields_ = [("tol", C.c_double), ("feas_tol", C.c_double), ("max_iter", C.c_int32), ("step_frac", C.c_double), ("device", C.c_int32)]
+    _fields_ = [("tol", C.c_double), ("feas_tol", C.c_double), ("max_iter", C.c_int32), ("step_frac", C.c_double),
+                ("device", C.c_int32), ("reg_primal", C.c_double), ("kernel", C.c_int32)]
+
+
+class _StageWB(C.Structure):
+    _fields_ = [("T", C.c_int32), ("a", C.c_double), ("binv", C.c_double), ("half", C.c_double), ("delta", C.c_double),
+                ("dur", C.c_double), ("k_rev", C.c_double), ("wcf_off", C.c_int32), ("p_off", C.c_int32),
+                ("col_idx", C.c_void_p), ("row_idx", C.c_void_p)]
 
 
 def load_library():
@@ -60,6 +69,8 @@ def load_library():
     lib.dsp_lp_template_create.restype = C.c_int
     lib.dsp_lp_template_destroy.argtypes = [C.c_void_p]
     lib.dsp_lp_template_destroy.restype = None
+    lib.dsp_lp_template_set_stage_wb.argtypes = [C.c_void_p, C.POINTER(_StageWB)]
+    lib.dsp_lp_template_set_stage_wb.restype = C.c_int
     lib.dsp_lp_default_opts.argtypes = [C.POINTER(_Opts)]
     lib.dsp_lp_default_opts.restype = None
     lib.dsp_lp_solve_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Opts),
@@ -105,7 +116,7 @@ def _f64(a):
 
 
 class BatchLPSolver:
-    def __init__(self, template: LPTemplate, tol=1e-9, feas_tol=1e-9, max_iter=60, step_frac=0.9995):
+    def __init__(self, template: LPTemplate, tol=1e-9, feas_tol=1e-9, max_iter=60, step_frac=0.9995, kernel=KERNEL_AUTO, reg_primal=1e-8):
         self.lib = load_library()
         self.t = template
         t = template
@@ -135,6 +146,17 @@ class BatchLPSolver:
         self.opts = _Opts()
         self.lib.dsp_lp_default_opts(C.byref(self.opts))
         self.opts.tol, self.opts.feas_tol, self.opts.max_iter, self.opts.step_frac = tol, feas_tol, max_iter, step_frac
+        self.opts.kernel = kernel
+        self.opts.reg_primal = reg_primal
+        st = t.meta.get("stage_wb")
+        self.has_stage = False
+        if st is not None and kernel != KERNEL_BAND:
+            ci, ri = _i32(st["col_idx"]), _i32(st["row_idx"])
+            sd = _StageWB(T=st["T"], a=st["a"], binv=st["binv"], half=st["half"], delta=st["delta"], dur=st["dur"],
+                          k_rev=st["k_rev"], wcf_off=st["wcf_off"], p_off=st["p_off"],
+                          col_idx=ci.ctypes.data_as(C.c_void_p), row_idx=ri.ctypes.data_as(C.c_void_p))
+            self._check(self.lib.dsp_lp_template_set_stage_wb(self.handle, C.byref(sd)), "dsp_lp_template_set_stage_wb")
+            self.has_stage = True
 
     def close(self):
         if getattr(self, "handle", None):

@@ -71,7 +71,19 @@ def wind_battery(T: int, extant_wind: bool = True) -> LPTemplate:
     B.obj_const((0.0, {iP: 1e-5 * (cap + PA * ann * T * BATT_OP_COST / 8760.0),
                        iW: 1e-5 * ((0.0 if extant_wind else WIND_CAP_COST) + PA * ann * T * WIND_OP_COST / 8760.0)}))
     B.meta.update(kind="wind_battery", T=T, ann=ann)
-    return B.build()
+    t = B.build()
+    if T <= 32:
+        # stage descriptor for the lane-per-period kernel (include/dsp_lp.h: dsp_stage_wb_desc)
+        cn = {n: j for j, n in enumerate(t.col_names)}
+        rn = {n: i for i, n in enumerate(t.row_names)}
+        col_idx = [[cn.get(f"blk[{k}].fs.splitter.grid_elec[0]", -1), cn.get(f"blk[{k}].fs.battery.elec_in[0]", -1),
+                    cn.get(f"blk[{k}].fs.battery.elec_out[0]", -1), cn.get(f"blk[{k}].fs.battery.state_of_charge[0]", -1),
+                    cn.get(f"blk[{k}].fs.battery.energy_throughput[0]", -1), cn.get(f"slack:soc_bound[{k}]", -1),
+                    cn.get(f"slack:wind[{k}]", -1)] for k in range(T)]
+        row_idx = [[rn[f"soc[{k}]"], rn[f"throughput[{k}]"], rn[f"soc_bound[{k}]"], rn[f"wind[{k}]"]] for k in range(T)]
+        t.meta["stage_wb"] = dict(T=T, a=ETA_C, binv=1.0 / ETA_D, half=0.5, delta=DEGRADATION, dur=DURATION, k_rev=k_rev,
+                                  wcf_off=0, p_off=iP, col_idx=np.array(col_idx, np.int32), row_idx=np.array(row_idx, np.int32))
+    return t
 
 
 def wind_battery_rparams(T, cf, wind_mw, batt_mw, pem_mw=None):

@@ -66,7 +66,26 @@ typedef struct {
     int32_t max_iter;     /* default 60                                                  */
     double  step_frac;    /* fraction of the step to the boundary (default 0.9995)       */
     int32_t device;       /* CUDA device ordinal, -1 = current                           */
+    double  reg_primal;   /* proximal regularisation of D^-1 in scaled units (default 1e-8): caps the scaling
+                             of never-binding columns (throughput, slacks) so A D A' stays factorisable    */
+    int32_t kernel;       /* DSP_KERNEL_AUTO (stage kernel when the template has one), _BAND, _STAGE */
 } dsp_opts;
+
+enum { DSP_KERNEL_AUTO = 0, DSP_KERNEL_BAND = 1, DSP_KERNEL_STAGE = 2 };
+
+/* Stage descriptor of the wind+battery price-taker flowsheet (wind_battery_LMP.py:172-267, reduced form):
+ * T <= 32 periods, per period the columns g,i,o,s,e,p,q and rows r1 (state_evolution, battery.py:145-149),
+ * r2 (accumulate_energy_throughput :151-153), r3 (state_of_charge_bounds :155-157, slack p),
+ * r4 (wind_power.py:120-122 + splitter, slack q).  Lets dsp_lp_solve_batch run the register-resident
+ * lane-per-period kernel instead of the generic band kernel; results are identical up to rounding.    */
+typedef struct {
+    int32_t T;
+    double a, binv, half, delta, dur;   /* charging_eta, 1/discharging_eta, 1/2, degradation_rate, duration  */
+    double k_rev;                       /* cost of g_t and o_t = k_rev * cparams[t]                          */
+    int32_t wcf_off, p_off;             /* rparams: wind_kw*cf_t at wcf_off+t, battery kW at p_off            */
+    const int32_t *col_idx;             /* [T*7] template column of (t, g,i,o,s,e,p,q), -1 if presolved away  */
+    const int32_t *row_idx;             /* [T*4] template row of (t, r1..r4)                                  */
+} dsp_stage_wb_desc;
 
 enum { DSP_OPTIMAL = 0, DSP_MAX_ITER = 1, DSP_NUMERICAL = 2 };
 enum { DSP_E_ARG = -1, DSP_E_CUDA = -2, DSP_E_SMEM = -3 };
@@ -74,6 +93,9 @@ enum { DSP_E_ARG = -1, DSP_E_CUDA = -2, DSP_E_SMEM = -3 };
 /* Replaces: the per-LP model hand-over inside SolverFactory(..).solve(m) (Pyomo LP/NL writer), done once. */
 int dsp_lp_template_create(const dsp_template_desc *desc, dsp_template **out);
 void dsp_lp_template_destroy(dsp_template *t);
+
+/* Optional: registers the stage structure of a wind+battery template (see dsp_stage_wb_desc). */
+int dsp_lp_template_set_stage_wb(dsp_template *t, const dsp_stage_wb_desc *d);
 
 void dsp_lp_default_opts(dsp_opts *o);
 

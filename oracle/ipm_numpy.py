@@ -17,7 +17,7 @@ import numpy as np
 OPTIMAL, MAXITER, NUMERR = 0, 1, 2
 
 
-def solve_batch(A, b, c, u, tol=1e-9, max_iter=60, eta=0.9995, verbose=False, start="simple", gap_floor=1e-4, feas_tol=None):
+def solve_batch(A, b, c, u, tol=1e-9, max_iter=60, eta=0.9995, verbose=False, start="simple", gap_floor=1e-4, feas_tol=None, rho=1e-8):
     """A: dense [m,n] shared;  b [N,m], c [N,n], u [N,n] (inf = none).  Returns dict(obj,x,y,status,iters)."""
     A = np.asarray(A, float)
     feas_tol = 1e-9 if feas_tol is None else feas_tol
@@ -86,7 +86,7 @@ def solve_batch(A, b, c, u, tol=1e-9, max_iter=60, eta=0.9995, verbose=False, st
             break
         ix = np.flatnonzero(active)
         xa, sa, za, wa, ya = x[ix], s[ix], z[ix], w[ix], y[ix]
-        d = 1.0 / (za / xa + np.where(bd, wa / sa, 0.0))
+        d = 1.0 / (za / xa + np.where(bd, wa / sa, 0.0) + rho)
         M = np.einsum("ij,nj,kj->nik", A, d, A, optimize=True)
         M[:, np.arange(m), np.arange(m)] *= (1.0 + 1e-14)
         try:

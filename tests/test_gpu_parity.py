@@ -94,6 +94,40 @@ def test_c2_full_batch_certificates(wb):
     assert gap.max() <= 2e-5 and gap.min() >= -1e-9
 
 
+def test_stage_and_band_kernels_agree(wb):
+    """Two independent CUDA implementations of the same algorithm: the generic band kernel (shared memory, band
+    LDL') and the stage kernel (registers, local elimination + twisted block LDL')."""
+    t, sol = wb
+    assert sol.has_stage
+    band = S.BatchLPSolver(t, kernel=S.KERNEL_BAND)
+    lmp, cf, W, P = SC.c2(2000)
+    rp = TP.wind_battery_rparams(24, cf, W, P)[0]
+    a = sol.solve_host(lmp, rp, want_x=True, want_y=True)
+    assert S.last_launch()["smem_bytes"] == 0                 # stage kernel: registers only
+    b = band.solve_host(lmp, rp, want_x=True, want_y=True)
+    assert S.last_launch()["smem_bytes"] > 0
+    assert (a.status == S.OPTIMAL).all() and (b.status == S.OPTIMAL).all()
+    assert rel_err(a.obj, b.obj).max() < 1e-7
+    assert (a.iters == b.iters).mean() > 0.97
+    scale = np.abs(t.instantiate(lmp[0], rp)[1]).max()
+    assert np.abs(a.x @ t.A.T - t.instantiate(lmp[0], rp)[1]).max() <= 1e-7 * scale
+
+
+def test_c5_design_sweep_sample_all_optimal(wb):
+    """BASELINE config 5 (64 design points x 8760 start hours), strided sample: degenerate hours with zero
+    capacity factor and 5 % batteries must still terminate optimal; spot-check against the oracle."""
+    t, sol = wb
+    lmp, cf, wind, batt = SC.c5()
+    sel = np.arange(0, lmp.shape[0], 23)
+    rp = TP.wind_battery_rparams(24, cf[sel], wind[sel], batt[sel])
+    r = sol.solve_host(lmp[sel], rp)
+    assert (r.status == S.OPTIMAL).all(), np.bincount(r.status)
+    assert r.iters.max() <= 40
+    chk = np.arange(0, sel.size, 211)
+    ref = np.array([H.solve(L.wind_battery_raw(lmp[sel[i]], cf[sel[i]], wind[sel[i]], batt[sel[i]]))[0] for i in chk])
+    assert rel_err(r.obj[chk], ref).max() < REL
+
+
 def test_price_scaling_is_linear_in_the_lp_part(wb):
     t, sol = wb
     lmp, cf, W, P = SC.c2(64)
