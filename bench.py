@@ -83,9 +83,17 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_run(lmp, cf, W, P, n_sample, procs=None):
     """The oracle loop (HiGHS dual simplex, constraints pre-built, cost vector swapped per LP) on all host cores."""
     from oracle import highs as H
+    procs = procs or host_cores()
     obj, dt, procs = H.solve_batch("wind_battery", lmp[:n_sample], kwargs=dict(cf=cf, wind_mw=W, batt_mw=P), procs=procs)
     return obj, dt, procs
 
@@ -95,7 +103,7 @@ def run_reference(args):
     if rank != 0:
         return
     lmp, cf, W, P, rp = workload(0)
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     per_step = int(min(BATCH, max(200, 250 * cores)))          # ~1 s of wall clock per step on all cores
     for _ in range(args.warmup):
         cpu_reference_run(lmp, cf, W, P, min(per_step, 64 * cores))
@@ -134,7 +142,7 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         lmp0, cf0, W0, P0, _ = workload(0)
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         n_sample = int(min(BATCH, max(500, 400 * cores)))
         cpu_reference_run(lmp0, cf0, W0, P0, min(n_sample, 16 * cores))          # warm-up (imports, page-in)
         ref, dt, procs = cpu_reference_run(lmp0, cf0, W0, P0, n_sample)

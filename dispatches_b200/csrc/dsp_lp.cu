@@ -476,7 +476,10 @@ namespace {
 #include "dsp_stage_wb.cuh"
 
 // stage kernel: one warp per LP, one lane per period, all state in registers (see dsp_stage_wb.cuh)
-__global__ void __launch_bounds__(128) dsp_ipm_stage_wb_kernel(const KParams P, const stagewb::StageParams S) {
+#ifndef DSP_STAGE_MINB
+#define DSP_STAGE_MINB 3
+#endif
+__global__ void __launch_bounds__(128, DSP_STAGE_MINB) dsp_ipm_stage_wb_kernel(const KParams P, const stagewb::StageParams S) {
     const int lane = threadIdx.x & 31;
     stagewb::Out O;
     O.obj = P.obj; O.x_out = P.x_out; O.y_out = P.y_out; O.status = P.status; O.iters = P.iters; O.n = P.n; O.m = P.m;
@@ -491,7 +494,10 @@ __global__ void __launch_bounds__(128) dsp_ipm_stage_wb_kernel(const KParams P, 
         for (int r = lane; r < P.Pr; r += 32) kconst += P.omap[r] * rp[r];
         for (int r = lane; r < P.Pc; r += 32) kconst += P.ocmap[r] * cp[r];
         kconst = stagewb::wsum(kconst) + P.o0;
-        stagewb::solve_one(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, P.step_frac, P.reg, P.max_iter, O, lane);
+        if (S.T == 24)
+            stagewb::solve_one<24>(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, P.step_frac, P.reg, P.max_iter, O, lane);
+        else
+            stagewb::solve_one<0>(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, P.step_frac, P.reg, P.max_iter, O, lane);
     }
 }
 

@@ -60,15 +60,14 @@ __device__ __forceinline__ double wsum(double v) {
 struct Sym2 { double a, b, c; };            // [[a, b], [b, c]]
 struct Mat2 { double a, b, c, d; };         // [[a, b], [c, d]]
 
-// inverse of an SPD 2x2 block through its LDL' factors (the adjugate formula loses the small pivot)
+// inverse of an SPD 2x2 block: adjugate / determinant, one reciprocal (the determinant keeps its accuracy through the
+// fused multiply-add; with the proximal regularisation the blocks are far from singular -- checked in the mirror)
 __device__ __forceinline__ Sym2 inv_spd(const Sym2 &D) {
-    const double i1 = frcp(D.a);
-    const double l = D.b * i1;
-    const double i2 = frcp(fma(-l, D.b, D.c));
+    const double i = frcp(fma(D.a, D.c, -(D.b * D.b)));
     Sym2 r;
-    r.c = i2;
-    r.b = -l * i2;
-    r.a = fma(l * l, i2, i1);
+    r.a = D.c * i;
+    r.b = -D.b * i;
+    r.c = D.a * i;
     return r;
 }
 __device__ __forceinline__ Mat2 mul_ss(const Sym2 &A, const Sym2 &B) {      // A * B
@@ -88,13 +87,17 @@ struct Factor {          // per-lane pieces of the twisted block LDL'
     Sym2 Dhinv;          // inverse of the eliminated diagonal block
     Mat2 G, G2;          // multipliers towards the outer neighbour(s) (G2: root only)
     Sym2 Cin;            // coupling to the inner neighbour (towards the root)
-    int src, fo, bsrc, bo, r, kmax, smax;
+    int src, fo, bsrc, bo;
     bool is_root;
 };
 
+template <int TT>
 __device__ __forceinline__ void tw_solve(const Factor &F, double &u1, double &u2, int T, int lane) {
+    constexpr int KU = TT > 0 ? 16 : 1;
+    const int r = T / 2, kmax = max(r - 1, T - 2 - r), smax = max(r, T - 1 - r);
     double g1 = u1, g2 = u2;
-    for (int k = 1; k <= F.kmax; ++k) {
+#pragma unroll KU
+    for (int k = 1; k <= kmax; ++k) {
         const double r1 = shfl_src(g1, F.src), r2 = shfl_src(g2, F.src);
         if (F.fo == k) {
             g1 -= fma(F.G.a, r1, F.G.b * r2);
@@ -102,11 +105,11 @@ __device__ __forceinline__ void tw_solve(const Factor &F, double &u1, double &u2
         }
     }
     {
-        const double a1 = shfl_src(g1, max(F.r - 1, 0)), a2 = shfl_src(g2, max(F.r - 1, 0));
-        const double b1 = shfl_src(g1, min(F.r + 1, 31)), b2 = shfl_src(g2, min(F.r + 1, 31));
+        const double a1 = shfl_src(g1, max(r - 1, 0)), a2 = shfl_src(g2, max(r - 1, 0));
+        const double b1 = shfl_src(g1, min(r + 1, 31)), b2 = shfl_src(g2, min(r + 1, 31));
         if (F.is_root) {
-            if (F.r >= 1) { g1 -= fma(F.G.a, a1, F.G.b * a2); g2 -= fma(F.G.c, a1, F.G.d * a2); }
-            if (F.r + 1 <= T - 1) { g1 -= fma(F.G2.a, b1, F.G2.b * b2); g2 -= fma(F.G2.c, b1, F.G2.d * b2); }
+            if (r >= 1) { g1 -= fma(F.G.a, a1, F.G.b * a2); g2 -= fma(F.G.c, a1, F.G.d * a2); }
+            if (r + 1 <= T - 1) { g1 -= fma(F.G2.a, b1, F.G2.b * b2); g2 -= fma(F.G2.c, b1, F.G2.d * b2); }
         }
     }
     u1 = 0.0; u2 = 0.0;
@@ -114,7 +117,8 @@ __device__ __forceinline__ void tw_solve(const Factor &F, double &u1, double &u2
         u1 = fma(F.Dhinv.a, g1, F.Dhinv.b * g2);
         u2 = fma(F.Dhinv.b, g1, F.Dhinv.c * g2);
     }
-    for (int s = 1; s <= F.smax; ++s) {
+#pragma unroll KU
+    for (int s = 1; s <= smax; ++s) {
         const double r1 = shfl_src(u1, F.bsrc), r2 = shfl_src(u2, F.bsrc);
         if (F.bo == s) {
             const double t1 = g1 - fma(F.Cin.a, r1, F.Cin.b * r2);
@@ -131,10 +135,11 @@ struct Out {
     int n, m;
 };
 
-// solves LP number p; all 32 lanes of the warp participate
+// solves LP number p; all 32 lanes of the warp participate.  TT > 0: horizon known at compile time (loops unroll)
+template <int TT>
 __device__ void solve_one(const StageParams &S, const double *cp, const double *rpar, double kconst, long long p,
                           double tol, double feas_tol, double step_frac, double reg, int max_iter, const Out &O, int lane) {
-    const int T = S.T;
+    const int T = TT > 0 ? TT : S.T;
     const bool act = lane < T, has_s = lane < T - 1;
     const double a = S.a, binv = S.binv, hf = S.hf, dl = S.dl;
     // ---- problem data of this period
@@ -159,14 +164,12 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
     double y1 = 0.0, y2 = 0.0, y3 = 0.0, y4 = 0.0;
     // ---- twisted elimination order
     Factor F;
-    F.r = T / 2;
-    F.is_root = (lane == F.r);
-    F.src = min(max(lane < F.r ? lane - 1 : lane + 1, 0), 31);
-    F.fo = (!act || F.is_root) ? 1 << 20 : (lane < F.r ? lane : T - 1 - lane);
-    F.kmax = max(F.r - 1, T - 2 - F.r);
-    F.bsrc = min(max(lane < F.r ? lane + 1 : lane - 1, 0), 31);
-    F.bo = (!act || F.is_root) ? 1 << 20 : abs(lane - F.r);
-    F.smax = max(F.r, T - 1 - F.r);
+    const int rt = T / 2, kmax = max(rt - 1, T - 2 - rt);
+    F.is_root = (lane == rt);
+    F.src = min(max(lane < rt ? lane - 1 : lane + 1, 0), 31);
+    F.fo = (!act || F.is_root) ? 1 << 20 : (lane < rt ? lane : T - 1 - lane);
+    F.bsrc = min(max(lane < rt ? lane + 1 : lane - 1, 0), 31);
+    F.bo = (!act || F.is_root) ? 1 << 20 : abs(lane - rt);
 
     int status = DSP_MAX_ITER, it = 0;
     double pobj = 0.0;
@@ -195,12 +198,12 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
         } else {
             rp1 = rp2 = rp3 = rp4 = rdg = rdi = rdo = rds = rde = rdp = rdq = rui = ruo = 0.0;
         }
-        pm = wmax(pm); dm = wmax(dm); mus = wsum(mus); po = wsum(po); dob = wsum(dob);
+        const double res = wmax(fmax(pm / nrm_b, dm / nrm_c));
+        mus = wsum(mus); po = wsum(po); dob = wsum(dob);
         pobj = po;
         const double mu = mus / ntot;
         const double den = fmax(kGapFloor, fabs(po));
         const double gap = fabs(po - dob) / den, cgap = ntot * mu / den;
-        const double res = fmax(pm / nrm_b, dm / nrm_c);
         if (!(mu == mu) || !(po == po) || mu > 1e100) { status = DSP_NUMERICAL; break; }
         if (res < feas_tol && gap < tol) { status = DSP_OPTIMAL; break; }
         if (cgap < tol && res < 10.0 * feas_tol && gap < 10.0 * tol) { status = DSP_OPTIMAL; break; }
@@ -236,14 +239,15 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
         Bn.a = (lane < T - 1) ? -s11 : 0.0; Bn.c = (lane < T - 1) ? -s22 : 0.0; Bn.b = (lane < T - 1) ? s12 : 0.0;
         Bp.a = -s11p; Bp.c = -s22p; Bp.b = s12p;
         if (!act) { D.a = 1.0; D.b = 0.0; D.c = 1.0; }
-        const Sym2 Cout = (lane < F.r) ? Bp : Bn;
-        F.Cin = (lane < F.r) ? Bn : Bp;
+        const Sym2 Cout = (lane < rt) ? Bp : Bn;
+        F.Cin = (lane < rt) ? Bn : Bp;
         // ---- twisted block LDL'
         Sym2 Dh = D;
         F.Dhinv = inv_spd(Dh);
         F.G.a = F.G.b = F.G.c = F.G.d = 0.0;
         F.G2 = F.G;
-        for (int k = 1; k <= F.kmax; ++k) {
+#pragma unroll (TT > 0 ? 16 : 1)
+        for (int k = 1; k <= kmax; ++k) {
             Sym2 R;
             R.a = shfl_src(F.Dhinv.a, F.src); R.b = shfl_src(F.Dhinv.b, F.src); R.c = shfl_src(F.Dhinv.c, F.src);
             if (F.fo == k) {
@@ -254,12 +258,12 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
         }
         {
             Sym2 Ra, Rb;
-            const int la = max(F.r - 1, 0), lb = min(F.r + 1, 31);
+            const int la = max(rt - 1, 0), lb = min(rt + 1, 31);
             Ra.a = shfl_src(F.Dhinv.a, la); Ra.b = shfl_src(F.Dhinv.b, la); Ra.c = shfl_src(F.Dhinv.c, la);
             Rb.a = shfl_src(F.Dhinv.a, lb); Rb.b = shfl_src(F.Dhinv.b, lb); Rb.c = shfl_src(F.Dhinv.c, lb);
             if (F.is_root) {
-                if (F.r >= 1) { F.G = mul_ss(Bp, Ra); sub_gc(Dh, F.G, Bp); }
-                if (F.r + 1 <= T - 1) { F.G2 = mul_ss(Bn, Rb); sub_gc(Dh, F.G2, Bn); }
+                if (rt >= 1) { F.G = mul_ss(Bp, Ra); sub_gc(Dh, F.G, Bp); }
+                if (rt + 1 <= T - 1) { F.G2 = mul_ss(Bn, Rb); sub_gc(Dh, F.G2, Bn); }
                 F.Dhinv = inv_spd(Dh);
             }
         }
@@ -287,7 +291,7 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
             double f1 = rp1 + ph1 - up1(ph1, lane) - a * psi + binv * doh;
             double f2 = rp2 + ph2 - up1(ph2, lane) - hf * psi - hf * doh;
             if (!act) { f1 = 0.0; f2 = 0.0; }
-            tw_solve(F, f1, f2, T, lane);
+            tw_solve<TT>(F, f1, f2, T, lane);
             dy1 = f1; dy2 = f2;
             const double e1 = dy1 - down1(dy1, lane) - hs, e2 = dy2 - down1(dy2, lane) - he;
             const double v = a * dy1 + hf * dy2;

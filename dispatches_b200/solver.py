@@ -17,7 +17,9 @@ import numpy as np
 
 from .lp_template import LPTemplate
 
-_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libdsp_lp.so"
+import os
+
+_LIB_PATH = Path(os.environ.get("DSP_LP_LIB", Path(__file__).resolve().parent / "csrc" / "libdsp_lp.so"))
 _lib = None
 
 OPTIMAL, MAX_ITER, NUMERICAL = 0, 1, 2

@@ -177,7 +177,7 @@ def nuclear(T: int = 48, np_capacity=500.0, pem_capacity=100.0, tank_capacity=50
             row[H[t - 1]] = -1.0
         B.eq(f"tank_balance[{t}]", row)
     B.meta.update(kind="nuclear", T=T, E=E)
-    return B.build()
+    return B.build(equilibrate=True)          # kW, mol/s and mol columns differ by 1e4: equilibrate (fewer iterations)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -227,4 +227,4 @@ def fossil_surrogate(T: int = 168, par=None) -> LPTemplate:
             B.le(f"ramp_up[{t}]", {pw[t]: 1.0}, P["ramp"] + P["pprev0"])
             B.le(f"ramp_down[{t}]", {pw[t]: -1.0}, P["ramp"] - P["pprev0"])
     B.meta.update(kind="fossil_surrogate", T=T)
-    return B.build()
+    return B.build(equilibrate=True)          # salt inventories (1e6 kg) next to powers (1e2 MW): must equilibrate
