@@ -84,10 +84,8 @@ class ClockSampler:
 
 
 def host_cores():
-    try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
+    from oracle import highs as H
+    return H.host_cores()
 
 
 def cpu_reference_run(lmp, cf, W, P, n_sample, procs=None):

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -739,7 +740,9 @@ int dsp_lp_solve_batch(const dsp_template *T, int64_t N, const double *cparams, 
     if (T->has_stage && o.kernel != DSP_KERNEL_BAND) {
         // stage kernel: no shared memory; persistent warps, one LP per warp at a time
         const int wpb = 4;
-        long long blocks = std::min<long long>((long long)T->sm_count * T->stage_blocks_per_sm, (N + wpb - 1) / wpb);
+        long long per_sm = T->stage_blocks_per_sm;
+        if (const char *e = getenv("DSP_STAGE_BLOCKS_PER_SM")) per_sm = std::max(1, atoi(e));   // experiments only
+        long long blocks = std::min<long long>((long long)T->sm_count * per_sm, (N + wpb - 1) / wpb);
         CK(cudaMemsetAsync(T->ticket, 0, sizeof(unsigned long long), st));
         dsp_ipm_stage_wb_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(K, T->sp);
         CK(cudaGetLastError());

@@ -26,15 +26,35 @@ from . import lp_models
 TIGHT = dict(primal_feasibility_tolerance=1e-10, dual_feasibility_tolerance=1e-10)
 
 
+def host_cores():
+    """cores this process may really use: scheduler affinity capped by the cgroup CPU quota (containers often expose
+    all host CPUs in the affinity mask but throttle to a few through cpu.max)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        txt = open("/sys/fs/cgroup/cpu.max").read().split()
+        if txt[0] != "max":
+            n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(q / p + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 def solve(lp: lp_models.RawLP, method="highs-ds"):
-    bounds = np.column_stack([lp.lb, lp.ub])
-    bounds = [(None if not np.isfinite(l) else l, None if not np.isfinite(u) else u) for l, u in bounds]
-    res = linprog(lp.c, A_ub=lp.A_ub if lp.A_ub.shape[0] else None, b_ub=lp.b_ub if lp.A_ub.shape[0] else None,
-                  A_eq=lp.A_eq if lp.A_eq.shape[0] else None, b_eq=lp.b_eq if lp.A_eq.shape[0] else None,
-                  bounds=bounds, method=method, options=dict(TIGHT))
-    if res.status != 0:
-        raise RuntimeError(f"HiGHS status {res.status}: {res.message}")
-    return float(res.fun + lp.c0), res.x
+    bounds = [(None if not np.isfinite(l) else l, None if not np.isfinite(u) else u) for l, u in zip(lp.lb, lp.ub)]
+    kw = dict(A_ub=lp.A_ub if lp.A_ub.shape[0] else None, b_ub=lp.b_ub if lp.A_ub.shape[0] else None,
+              A_eq=lp.A_eq if lp.A_eq.shape[0] else None, b_eq=lp.b_eq if lp.A_eq.shape[0] else None, bounds=bounds)
+    # tight dual simplex first; HiGHS occasionally mis-reports a badly scaled LP (fossil surrogate, 1e6-kg inventories)
+    # as unbounded under 1e-10 tolerances -> fall back to its interior point, then to default tolerances
+    for m, opts in ((method, TIGHT), ("highs-ipm", TIGHT), (method, {})):
+        res = linprog(lp.c, method=m, options=dict(opts), **kw)
+        if res.status == 0:
+            return float(res.fun + lp.c0), res.x
+    raise RuntimeError(f"HiGHS status {res.status}: {res.message}")
 
 
 # ---- batched loop used as the CPU baseline: the constraint data are built once per worker, only the
@@ -82,7 +102,7 @@ def solve_batch(kind, lmps, extras=None, kwargs=None, procs=None):
     """Objective of every LP of a batch; ``procs`` worker processes (default: all host cores).
     Returns (obj[N], seconds, procs)."""
     kwargs = kwargs or {}
-    procs = procs or len(os.sched_getaffinity(0))
+    procs = procs or host_cores()
     lmps = np.asarray(lmps, float)
     N = lmps.shape[0]
     chunks = np.array_split(np.arange(N), max(1, min(N, procs * 4)))

@@ -184,7 +184,7 @@ class PCR:
         return _mv(self.Dinv, F)[:, :self.T]
 
 
-def solve_batch(lmp, wcf, P, consts, tol=1e-9, feas_tol=1e-9, max_iter=60, eta=0.9995, gap_floor=1e-4, verbose=False, rho=1e-8):
+def solve_batch(lmp, wcf, P, consts, tol=1e-9, feas_tol=1e-9, max_iter=60, eta=0.9995, gap_floor=1e-4, verbose=False, rho=1e-8, start=None, stop_mu=None, start_mode=0):
     """lmp [N,T] $/MWh; wcf [N,T] = wind_kw*cf (kW); P [N] battery kW.
     consts: dict(a, binv, half, delta, dur, k_rev) taken from the LP template.
     Returns dict(obj_lp [N] (= c'x, without the design constant), status, iters, g,i,o,s,e [N,T])."""
@@ -207,6 +207,23 @@ def solve_batch(lmp, wcf, P, consts, tol=1e-9, feas_tol=1e-9, max_iter=60, eta=0
     x["s"] = x["s"] * hs; z["s"] = z["s"] * hs
     sb = {k: u - x[k] for k in "io"}; wb = {k: one.copy() for k in "io"}
     y = {k: np.zeros((N, T)) for k in (1, 2, 3, 4)}
+    if start_mode >= 1:          # experiment: primal start that satisfies the two local rows exactly
+        th = 0.5
+        x["g"] = np.maximum(th * b4, 1e-2); x["i"] = np.minimum(np.minimum(1.0, 0.5 * u), np.maximum(0.25 * b4, 1e-2)); x["o"] = x["i"].copy()
+        x["q"] = np.maximum(b4 - x["g"] - x["i"], 1e-2)
+        x["s"] = np.maximum(0.5 * b3, 1e-2) * hs; x["e"] = np.maximum(0.5 * np.cumsum(x["i"] + x["o"], axis=1), 1e-2)
+        x["p"] = np.maximum(b3 - x["s"] - dl * x["e"], 1e-2)
+        sb = {k: u - x[k] for k in "io"}
+    if start_mode >= 2:
+        mu0 = 0.1
+        for k in "giosepq":
+            z[k] = np.where(x[k] > 0, mu0 / np.where(x[k] > 0, x[k], 1.0), 0.0)
+        for k in "io":
+            wb[k] = mu0 / sb[k]
+    if start is not None:        # experiment: common warm start (scaled iterate of a representative LP)
+        x = {k: np.repeat(start["x"][k], N, 0) for k in "giosepq"}; z = {k: np.repeat(start["z"][k], N, 0) for k in "giosepq"}
+        sb = {k: np.repeat(start["sb"][k], N, 0) for k in "io"}; wb = {k: np.repeat(start["wb"][k], N, 0) for k in "io"}
+        y = {k: np.repeat(start["y"][k], N, 0) for k in (1, 2, 3, 4)}
     ntot = 7 * T - 1 + 2 * T
     status = np.full(N, MAXITER); iters = np.full(N, max_iter)
     active = np.ones(N, bool)
@@ -247,6 +264,8 @@ def solve_batch(lmp, wcf, P, consts, tol=1e-9, feas_tol=1e-9, max_iter=60, eta=0
                   "rd", " ".join("%s %.1e" % (k, np.abs(v).max()) for k, v in rd.items()))
         if not active.any() or it == max_iter:
             break
+        if stop_mu is not None and mu.max() < stop_mu:
+            return dict(x=x, z=z, sb=sb, wb=wb, y=y, it=it)
         # ---- scaling matrix
         with np.errstate(divide="ignore", invalid="ignore"):
             d = {k: 1.0 / (z[k] / x[k] + rho) for k in "gepq"}
