@@ -480,7 +480,10 @@ namespace {
 #ifndef DSP_STAGE_MINB
 #define DSP_STAGE_MINB 3
 #endif
-__global__ void __launch_bounds__(128, DSP_STAGE_MINB) dsp_ipm_stage_wb_kernel(const KParams P, const stagewb::StageParams S) {
+#ifndef DSP_STAGE_WPB
+#define DSP_STAGE_WPB 4
+#endif
+__global__ void __launch_bounds__(32 * DSP_STAGE_WPB, DSP_STAGE_MINB) dsp_ipm_stage_wb_kernel(const KParams P, const stagewb::StageParams S) {
     const int lane = threadIdx.x & 31;
     stagewb::Out O;
     O.obj = P.obj; O.x_out = P.x_out; O.y_out = P.y_out; O.status = P.status; O.iters = P.iters; O.n = P.n; O.m = P.m;
@@ -495,10 +498,19 @@ __global__ void __launch_bounds__(128, DSP_STAGE_MINB) dsp_ipm_stage_wb_kernel(c
         for (int r = lane; r < P.Pr; r += 32) kconst += P.omap[r] * rp[r];
         for (int r = lane; r < P.Pc; r += 32) kconst += P.ocmap[r] * cp[r];
         kconst = stagewb::wsum(kconst) + P.o0;
-        if (S.T == 24)
-            stagewb::solve_one<24>(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, P.step_frac, P.reg, P.max_iter, O, lane);
-        else
-            stagewb::solve_one<0>(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, P.step_frac, P.reg, P.max_iter, O, lane);
+        // second attempt with a shorter step and a stronger proximal term for the (1 in 1e5) LPs whose first attempt ends
+        // non-optimal: the rounding floor of the last iterations differs from LP to LP
+        int it0 = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const double sf = attempt ? 0.99 : P.step_frac, rg = attempt ? 10.0 * P.reg : P.reg;
+            int r;
+            if (S.T == 24)
+                r = stagewb::solve_one<24>(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, sf, rg, P.max_iter, O, lane, it0);
+            else
+                r = stagewb::solve_one<0>(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, sf, rg, P.max_iter, O, lane, it0);
+            if (r == 0) break;
+            it0 = r - 1;
+        }
     }
 }
 
@@ -548,7 +560,7 @@ struct dsp_template {
     int32_t *d_status, *d_iters;
     bool cap_x, cap_y;
     int64_t cap_rp_rows;
-    cudaStream_t stream;
+    cudaStream_t stream, stream2;
 };
 
 extern "C" {
@@ -625,7 +637,7 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     T->has_stage = false; T->stage_blocks_per_sm = 0;
     T->h_cp = T->h_rp = T->h_obj = T->h_x = T->h_y = nullptr; T->h_status = T->h_iters = nullptr;
     T->d_cp = T->d_rp = T->d_obj = T->d_x = T->d_y = nullptr; T->d_status = T->d_iters = nullptr;
-    T->stream = nullptr;
+    T->stream = nullptr; T->stream2 = nullptr;
     CK(cudaGetDevice(&T->device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, T->device));
@@ -676,11 +688,12 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     rc |= up_i(D->umap.idx, D->umap.ptr[nb], &K.um_idx);
     rc |= up_d(D->umap.val, D->umap.ptr[nb], &K.um_val);
     if (rc) return DSP_E_CUDA;
-    CK(cudaMalloc((void **)&T->ticket, sizeof(unsigned long long)));
+    CK(cudaMalloc((void **)&T->ticket, 16 * sizeof(unsigned long long)));
     T->dev_allocs.push_back(T->ticket);
     K.prob_doubles = 7 * n + 5 * nb + 4 * m + m * (w + 1);
     CK(cudaFuncSetAttribute(dsp_ipm_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaStreamCreateWithFlags(&T->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&T->stream2, cudaStreamNonBlocking));
     *out = T;
     return 0;
 }
@@ -703,7 +716,7 @@ int dsp_lp_template_set_stage_wb(dsp_template *T, const dsp_stage_wb_desc *d) {
     T->dev_allocs.push_back(dci); T->dev_allocs.push_back(dri);
     S.col_idx = dci; S.row_idx = dri;
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dsp_ipm_stage_wb_kernel, 128, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dsp_ipm_stage_wb_kernel, 32 * DSP_STAGE_WPB, 0));
     T->stage_blocks_per_sm = std::max(nb, 1);
     T->has_stage = true;
     return 0;
@@ -717,12 +730,13 @@ void dsp_lp_template_destroy(dsp_template *T) {
     cudaFreeHost(T->h_cp); cudaFreeHost(T->h_rp); cudaFreeHost(T->h_obj); cudaFreeHost(T->h_x); cudaFreeHost(T->h_y);
     cudaFreeHost(T->h_status); cudaFreeHost(T->h_iters);
     if (T->stream) cudaStreamDestroy(T->stream);
+    if (T->stream2) cudaStreamDestroy(T->stream2);
     delete T;
 }
 
-int dsp_lp_solve_batch(const dsp_template *T, int64_t N, const double *cparams, const double *rparams,
-                       int64_t rparams_stride, const dsp_opts *opts, double *obj, int32_t *status, int32_t *iters,
-                       double *x, double *y, void *cuda_stream) {
+static int launch_batch(const dsp_template *T, int64_t N, const double *cparams, const double *rparams,
+                        int64_t rparams_stride, const dsp_opts *opts, double *obj, int32_t *status, int32_t *iters,
+                        double *x, double *y, void *cuda_stream, unsigned long long *ticket) {
     if (!T || N < 0 || !obj || !status || !iters || (T->kp.Pc > 0 && !cparams) || (T->kp.Pr > 0 && !rparams)) {
         g_err = "dsp_lp_solve_batch: bad arguments";
         return DSP_E_ARG;
@@ -736,14 +750,14 @@ int dsp_lp_solve_batch(const dsp_template *T, int64_t N, const double *cparams, 
     K.N = N; K.cparams = cparams; K.rparams = rparams; K.rstride = rparams_stride;
     K.tol = o.tol; K.feas_tol = o.feas_tol; K.step_frac = o.step_frac; K.reg = o.reg_primal; K.max_iter = o.max_iter;
     K.obj = obj; K.status = status; K.iters = iters; K.x_out = x; K.y_out = y;
-    K.ticket = T->ticket;
+    K.ticket = ticket;
     if (T->has_stage && o.kernel != DSP_KERNEL_BAND) {
         // stage kernel: no shared memory; persistent warps, one LP per warp at a time
-        const int wpb = 4;
+        const int wpb = DSP_STAGE_WPB;
         long long per_sm = T->stage_blocks_per_sm;
         if (const char *e = getenv("DSP_STAGE_BLOCKS_PER_SM")) per_sm = std::max(1, atoi(e));   // experiments only
         long long blocks = std::min<long long>((long long)T->sm_count * per_sm, (N + wpb - 1) / wpb);
-        CK(cudaMemsetAsync(T->ticket, 0, sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
         dsp_ipm_stage_wb_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(K, T->sp);
         CK(cudaGetLastError());
         std::lock_guard<std::mutex> lk(g_mu);
@@ -780,7 +794,7 @@ int dsp_lp_solve_batch(const dsp_template *T, int64_t N, const double *cparams, 
     K.hot_in_smem = hot_in_smem;
     K.prob_off = (int)off;
     const size_t smem = off + (size_t)warps * prob_bytes;
-    CK(cudaMemsetAsync(T->ticket, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
     dsp_ipm_band_kernel<<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
     CK(cudaGetLastError());
     {
@@ -789,6 +803,13 @@ int dsp_lp_solve_batch(const dsp_template *T, int64_t N, const double *cparams, 
         g_last_grid = (int)ctas; g_last_block = (int)(warps * 32); g_last_smem = (int)smem; g_last_ppc = (int)warps;
     }
     return 0;
+}
+
+int dsp_lp_solve_batch(const dsp_template *T, int64_t N, const double *cparams, const double *rparams,
+                       int64_t rparams_stride, const dsp_opts *opts, double *obj, int32_t *status, int32_t *iters,
+                       double *x, double *y, void *cuda_stream) {
+    return launch_batch(T, N, cparams, rparams, rparams_stride, opts, obj, status, iters, x, y, cuda_stream,
+                        T ? T->ticket : nullptr);
 }
 
 static int ensure_capacity(dsp_template *T, int64_t N, int64_t rp_rows, bool want_x, bool want_y) {
@@ -824,29 +845,48 @@ int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, c
     const int64_t rp_rows = (rparams_stride == 0) ? 1 : N;
     int rc = ensure_capacity(T, N, rp_rows, x != nullptr, y != nullptr);
     if (rc) return rc;
-    cudaStream_t st = T->stream;
-    if (K.Pc > 0) {
-        memcpy(T->h_cp, cparams, (size_t)N * K.Pc * 8);
-        CK(cudaMemcpyAsync(T->d_cp, T->h_cp, (size_t)N * K.Pc * 8, cudaMemcpyHostToDevice, st));
-    }
+    // chunked pipeline over two streams: the pinned-staging memcpy + H2D of chunk k+1 and the D2H of chunk k-1 overlap
+    // the kernel of chunk k.  The shared rparams row (stride 0) goes first on stream 1; an event orders stream 2 after it.
+    cudaStream_t sts[2] = {T->stream, T->stream2};
     int64_t dstride = 0;
-    if (K.Pr > 0) {
-        if (rparams_stride != 0 && rparams_stride != K.Pr) {   // compact strided rows
-            for (int64_t r = 0; r < rp_rows; ++r) memcpy(T->h_rp + r * K.Pr, rparams + r * rparams_stride, (size_t)K.Pr * 8);
-        } else {
-            memcpy(T->h_rp, rparams, (size_t)rp_rows * K.Pr * 8);
-        }
-        CK(cudaMemcpyAsync(T->d_rp, T->h_rp, (size_t)rp_rows * K.Pr * 8, cudaMemcpyHostToDevice, st));
-        dstride = (rparams_stride == 0) ? 0 : K.Pr;
+    const bool shared_rp = (K.Pr > 0 && rparams_stride == 0);
+    if (shared_rp) {
+        memcpy(T->h_rp, rparams, (size_t)K.Pr * 8);
+        CK(cudaMemcpyAsync(T->d_rp, T->h_rp, (size_t)K.Pr * 8, cudaMemcpyHostToDevice, sts[0]));
+        CK(cudaStreamSynchronize(sts[0]));          // 0.2 KB, makes the row visible to both streams
+    } else if (K.Pr > 0) {
+        dstride = K.Pr;
     }
-    rc = dsp_lp_solve_batch(T, N, T->d_cp, T->d_rp, dstride, opts, T->d_obj, T->d_status, T->d_iters,
-                            x ? T->d_x : nullptr, y ? T->d_y : nullptr, st);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(T->h_obj, T->d_obj, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(T->h_status, T->d_status, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(T->h_iters, T->d_iters, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
-    if (x) CK(cudaMemcpyAsync(T->h_x, T->d_x, (size_t)N * K.n * 8, cudaMemcpyDeviceToHost, st));
-    if (y) CK(cudaMemcpyAsync(T->h_y, T->d_y, (size_t)N * K.m * 8, cudaMemcpyDeviceToHost, st));
+    const int nchunk = (int)std::min<int64_t>(8, std::max<int64_t>(1, N / 2048));
+    const int64_t per = (N + nchunk - 1) / nchunk;
+    for (int c = 0; c < nchunk; ++c) {
+        const int64_t lo = c * per, cnt = std::min<int64_t>(per, N - lo);
+        if (cnt <= 0) break;
+        cudaStream_t st = sts[c & 1];
+        if (K.Pc > 0) {
+            memcpy(T->h_cp + lo * K.Pc, cparams + lo * K.Pc, (size_t)cnt * K.Pc * 8);
+            CK(cudaMemcpyAsync(T->d_cp + lo * K.Pc, T->h_cp + lo * K.Pc, (size_t)cnt * K.Pc * 8, cudaMemcpyHostToDevice, st));
+        }
+        if (K.Pr > 0 && !shared_rp) {
+            if (rparams_stride != K.Pr) {   // compact strided rows
+                for (int64_t r = 0; r < cnt; ++r) memcpy(T->h_rp + (lo + r) * K.Pr, rparams + (lo + r) * rparams_stride, (size_t)K.Pr * 8);
+            } else {
+                memcpy(T->h_rp + lo * K.Pr, rparams + lo * K.Pr, (size_t)cnt * K.Pr * 8);
+            }
+            CK(cudaMemcpyAsync(T->d_rp + lo * K.Pr, T->h_rp + lo * K.Pr, (size_t)cnt * K.Pr * 8, cudaMemcpyHostToDevice, st));
+        }
+        rc = launch_batch(T, cnt, T->d_cp + lo * K.Pc, shared_rp ? T->d_rp : T->d_rp + lo * K.Pr, dstride, opts,
+                          T->d_obj + lo, T->d_status + lo, T->d_iters + lo, x ? T->d_x + lo * K.n : nullptr,
+                          y ? T->d_y + lo * K.m : nullptr, st, T->ticket + c);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(T->h_obj + lo, T->d_obj + lo, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(T->h_status + lo, T->d_status + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(T->h_iters + lo, T->d_iters + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        if (x) CK(cudaMemcpyAsync(T->h_x + lo * K.n, T->d_x + lo * K.n, (size_t)cnt * K.n * 8, cudaMemcpyDeviceToHost, st));
+        if (y) CK(cudaMemcpyAsync(T->h_y + lo * K.m, T->d_y + lo * K.m, (size_t)cnt * K.m * 8, cudaMemcpyDeviceToHost, st));
+    }
+    cudaStream_t st = sts[0];
+    CK(cudaStreamSynchronize(sts[1]));
     CK(cudaStreamSynchronize(st));
     memcpy(obj, T->h_obj, (size_t)N * 8);
     memcpy(status, T->h_status, (size_t)N * 4);

@@ -51,6 +51,16 @@ __device__ __forceinline__ double wmax(double v) {
     for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// max over the warp of NON-NEGATIVE doubles with two 32-bit hardware reductions (redux.sync) instead of five
+// shuffle levels: for v >= 0 the IEEE bit pattern is monotone, so reduce the high words, then the low words of the
+// lanes that hold the maximal high word
+__device__ __forceinline__ double wmax_pos(double v) {
+    v = v > 0.0 ? v : 0.0;          // negatives and -0.0 would win the unsigned comparison
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -91,11 +101,33 @@ struct Factor {          // per-lane pieces of the twisted block LDL'
     bool is_root;
 };
 
+// backward half of the solve: on entry (g1, g2) is the forward-eliminated right-hand side, on exit the solution
 template <int TT>
-__device__ __forceinline__ void tw_solve(const Factor &F, double &u1, double &u2, int T, int lane) {
+__device__ __forceinline__ void tw_back(const Factor &F, double &g1, double &g2, int T, int lane) {
     constexpr int KU = TT > 0 ? 16 : 1;
-    const int r = T / 2, kmax = max(r - 1, T - 2 - r), smax = max(r, T - 1 - r);
-    double g1 = u1, g2 = u2;
+    const int r = T / 2, smax = max(r, T - 1 - r);
+    double u1 = 0.0, u2 = 0.0;
+    if (F.is_root) {
+        u1 = fma(F.Dhinv.a, g1, F.Dhinv.b * g2);
+        u2 = fma(F.Dhinv.b, g1, F.Dhinv.c * g2);
+    }
+#pragma unroll KU
+    for (int s = 1; s <= smax; ++s) {
+        const double r1 = shfl_src(u1, F.bsrc), r2 = shfl_src(u2, F.bsrc);
+        if (F.bo == s) {
+            const double t1 = g1 - fma(F.Cin.a, r1, F.Cin.b * r2);
+            const double t2 = g2 - fma(F.Cin.b, r1, F.Cin.c * r2);
+            u1 = fma(F.Dhinv.a, t1, F.Dhinv.b * t2);
+            u2 = fma(F.Dhinv.b, t1, F.Dhinv.c * t2);
+        }
+    }
+    g1 = u1; g2 = u2;
+}
+
+template <int TT>
+__device__ __forceinline__ void tw_solve(const Factor &F, double &g1, double &g2, int T, int lane) {
+    constexpr int KU = TT > 0 ? 16 : 1;
+    const int r = T / 2, kmax = max(r - 1, T - 2 - r);
 #pragma unroll KU
     for (int k = 1; k <= kmax; ++k) {
         const double r1 = shfl_src(g1, F.src), r2 = shfl_src(g2, F.src);
@@ -112,21 +144,7 @@ __device__ __forceinline__ void tw_solve(const Factor &F, double &u1, double &u2
             if (r + 1 <= T - 1) { g1 -= fma(F.G2.a, b1, F.G2.b * b2); g2 -= fma(F.G2.c, b1, F.G2.d * b2); }
         }
     }
-    u1 = 0.0; u2 = 0.0;
-    if (F.is_root) {
-        u1 = fma(F.Dhinv.a, g1, F.Dhinv.b * g2);
-        u2 = fma(F.Dhinv.b, g1, F.Dhinv.c * g2);
-    }
-#pragma unroll KU
-    for (int s = 1; s <= smax; ++s) {
-        const double r1 = shfl_src(u1, F.bsrc), r2 = shfl_src(u2, F.bsrc);
-        if (F.bo == s) {
-            const double t1 = g1 - fma(F.Cin.a, r1, F.Cin.b * r2);
-            const double t2 = g2 - fma(F.Cin.b, r1, F.Cin.c * r2);
-            u1 = fma(F.Dhinv.a, t1, F.Dhinv.b * t2);
-            u2 = fma(F.Dhinv.b, t1, F.Dhinv.c * t2);
-        }
-    }
+    tw_back<TT>(F, g1, g2, T, lane);
 }
 
 struct Out {
@@ -137,8 +155,8 @@ struct Out {
 
 // solves LP number p; all 32 lanes of the warp participate.  TT > 0: horizon known at compile time (loops unroll)
 template <int TT>
-__device__ void solve_one(const StageParams &S, const double *cp, const double *rpar, double kconst, long long p,
-                          double tol, double feas_tol, double step_frac, double reg, int max_iter, const Out &O, int lane) {
+__device__ int solve_one(const StageParams &S, const double *cp, const double *rpar, double kconst, long long p,
+                          double tol, double feas_tol, double step_frac, double reg, int max_iter, const Out &O, int lane, int it0) {
     const int T = TT > 0 ? TT : S.T;
     const bool act = lane < T, has_s = lane < T - 1;
     const double a = S.a, binv = S.binv, hf = S.hf, dl = S.dl;
@@ -148,10 +166,10 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
     const double P = rpar[S.p_off];
     double c = S.krev * lam;
     double b3 = S.dur * P, b4 = wcf;
-    const double b4max = wmax(fabs(b4));
+    const double b4max = wmax_pos(fabs(b4));
     double beta_b = fmax(fmax(fabs(b3), b4max), P);
     beta_b = beta_b > 0.0 ? beta_b : 1.0;
-    const double cmax = wmax(fabs(c));
+    const double cmax = wmax_pos(fabs(c));
     const double beta_c = cmax > 0.0 ? cmax : 1.0;
     c = c / beta_c; b3 = b3 / beta_b; b4 = b4 / beta_b;
     const double u = fmax(P / beta_b, 1e-10);
@@ -198,7 +216,7 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
         } else {
             rp1 = rp2 = rp3 = rp4 = rdg = rdi = rdo = rds = rde = rdp = rdq = rui = ruo = 0.0;
         }
-        const double res = wmax(fmax(pm / nrm_b, dm / nrm_c));
+        const double res = wmax_pos(fmax(pm / nrm_b, dm / nrm_c));
         mus = wsum(mus); po = wsum(po); dob = wsum(dob);
         pobj = po;
         const double mu = mus / ntot;
@@ -241,39 +259,14 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
         if (!act) { D.a = 1.0; D.b = 0.0; D.c = 1.0; }
         const Sym2 Cout = (lane < rt) ? Bp : Bn;
         F.Cin = (lane < rt) ? Bn : Bp;
-        // ---- twisted block LDL'
-        Sym2 Dh = D;
-        F.Dhinv = inv_spd(Dh);
-        F.G.a = F.G.b = F.G.c = F.G.d = 0.0;
-        F.G2 = F.G;
-#pragma unroll (TT > 0 ? 16 : 1)
-        for (int k = 1; k <= kmax; ++k) {
-            Sym2 R;
-            R.a = shfl_src(F.Dhinv.a, F.src); R.b = shfl_src(F.Dhinv.b, F.src); R.c = shfl_src(F.Dhinv.c, F.src);
-            if (F.fo == k) {
-                F.G = mul_ss(Cout, R);
-                sub_gc(Dh, F.G, Cout);
-                F.Dhinv = inv_spd(Dh);
-            }
-        }
-        {
-            Sym2 Ra, Rb;
-            const int la = max(rt - 1, 0), lb = min(rt + 1, 31);
-            Ra.a = shfl_src(F.Dhinv.a, la); Ra.b = shfl_src(F.Dhinv.b, la); Ra.c = shfl_src(F.Dhinv.c, la);
-            Rb.a = shfl_src(F.Dhinv.a, lb); Rb.b = shfl_src(F.Dhinv.b, lb); Rb.c = shfl_src(F.Dhinv.c, lb);
-            if (F.is_root) {
-                if (rt >= 1) { F.G = mul_ss(Bp, Ra); sub_gc(Dh, F.G, Bp); }
-                if (rt + 1 <= T - 1) { F.G2 = mul_ss(Bn, Rb); sub_gc(Dh, F.G2, Bn); }
-                F.Dhinv = inv_spd(Dh);
-            }
-        }
         const double dsk = ds * kap, dek = dl * de * kap, dii = di * iot;
-        // ---- Newton direction for complementarity targets ax (x z -> ax), as (s w -> as)
+        // ---- Newton right-hand side for complementarity targets ax (x z -> ax), as (s w -> as)
         double dxg, dxi, dxo, dxs, dxe, dxp, dxq, dy1, dy2, dy3, dy4;
         double cg = 0, ci = 0, co = 0, cs = 0, ce = 0, cpp = 0, cq = 0, csi = 0, cso = 0;   // predictor products
         double smu = 0.0;
-        auto newton = [&](bool corr) {
-            double hg = rdg + zg, hi = rdi + zi, ho = rdo + zo, hs = rds + zs, he = rde + ze, hp = rdp + zp, hq = rdq + zq;
+        double hg, hi, ho, hs, he, hp, hq, w3, w4;
+        auto make_rhs = [&](bool corr, double &f1, double &f2) {
+            hg = rdg + zg; hi = rdi + zi; ho = rdo + zo; hs = rds + zs; he = rde + ze; hp = rdp + zp; hq = rdq + zq;
             double asi = -wi * rui, aso = -wo * ruo;
             if (corr) {
                 hg -= (smu - cg) * rxg; hi -= (smu - ci) * rxi; ho -= (smu - co) * rxo; hs -= (smu - cs) * rxs;
@@ -282,17 +275,18 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
             }
             hi += asi * rsi - wi; ho += aso * rso - wo;
             if (!has_s) hs = 0.0;
-            const double w3 = rp3 + dp * hp;
+            w3 = rp3 + dp * hp;
             const double ph1 = s11 * hs - s12 * he - dsk * w3;
             const double ph2 = s22 * he - s12 * hs - dek * w3;
-            const double w4 = rp4 + dg * hg + dq * hq;
+            w4 = rp4 + dg * hg + dq * hq;
             const double psi = tau * hi - dii * w4;
             const double doh = dO * ho;
-            double f1 = rp1 + ph1 - up1(ph1, lane) - a * psi + binv * doh;
-            double f2 = rp2 + ph2 - up1(ph2, lane) - hf * psi - hf * doh;
+            f1 = rp1 + ph1 - up1(ph1, lane) - a * psi + binv * doh;
+            f2 = rp2 + ph2 - up1(ph2, lane) - hf * psi - hf * doh;
             if (!act) { f1 = 0.0; f2 = 0.0; }
-            tw_solve<TT>(F, f1, f2, T, lane);
-            dy1 = f1; dy2 = f2;
+        };
+        auto recover = [&](double u1, double u2) {
+            dy1 = u1; dy2 = u2;
             const double e1 = dy1 - down1(dy1, lane) - hs, e2 = dy2 - down1(dy2, lane) - he;
             const double v = a * dy1 + hf * dy2;
             dxs = has_s ? s11 * e1 - s12 * e2 + dsk * w3 : 0.0;
@@ -305,8 +299,49 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
             dxp = dp * (dy3 - hp);
             dxq = dq * (dy4 - hq);
         };
+        // ---- twisted block LDL'; the forward elimination of the PREDICTOR right-hand side rides along in the same
+        // ---- sweep (its shuffles and FMAs fill the latency shadow of the 2x2 inversions)
+        double g1, g2;
+        make_rhs(false, g1, g2);
+        Sym2 Dh = D;
+        F.Dhinv = inv_spd(Dh);
+        F.G.a = F.G.b = F.G.c = F.G.d = 0.0;
+        F.G2 = F.G;
+#pragma unroll (TT > 0 ? 16 : 1)
+        for (int k = 1; k <= kmax; ++k) {
+            Sym2 R;
+            R.a = shfl_src(F.Dhinv.a, F.src); R.b = shfl_src(F.Dhinv.b, F.src); R.c = shfl_src(F.Dhinv.c, F.src);
+            const double q1 = shfl_src(g1, F.src), q2 = shfl_src(g2, F.src);
+            if (F.fo == k) {
+                F.G = mul_ss(Cout, R);
+                g1 -= fma(F.G.a, q1, F.G.b * q2);
+                g2 -= fma(F.G.c, q1, F.G.d * q2);
+                sub_gc(Dh, F.G, Cout);
+                F.Dhinv = inv_spd(Dh);
+            }
+        }
+        {
+            Sym2 Ra, Rb;
+            const int la = max(rt - 1, 0), lb = min(rt + 1, 31);
+            Ra.a = shfl_src(F.Dhinv.a, la); Ra.b = shfl_src(F.Dhinv.b, la); Ra.c = shfl_src(F.Dhinv.c, la);
+            Rb.a = shfl_src(F.Dhinv.a, lb); Rb.b = shfl_src(F.Dhinv.b, lb); Rb.c = shfl_src(F.Dhinv.c, lb);
+            const double a1 = shfl_src(g1, la), a2 = shfl_src(g2, la), b1 = shfl_src(g1, lb), b2 = shfl_src(g2, lb);
+            if (F.is_root) {
+                if (rt >= 1) {
+                    F.G = mul_ss(Bp, Ra); sub_gc(Dh, F.G, Bp);
+                    g1 -= fma(F.G.a, a1, F.G.b * a2); g2 -= fma(F.G.c, a1, F.G.d * a2);
+                }
+                if (rt + 1 <= T - 1) {
+                    F.G2 = mul_ss(Bn, Rb); sub_gc(Dh, F.G2, Bn);
+                    g1 -= fma(F.G2.a, b1, F.G2.b * b2); g2 -= fma(F.G2.c, b1, F.G2.d * b2);
+                }
+                F.Dhinv = inv_spd(Dh);
+            }
+        }
+        // ---- affine predictor: backward sweep only
+        tw_back<TT>(F, g1, g2, T, lane);
+        recover(g1, g2);
         // dz = ax/x - z - z dx / x ;  dw = as/s - w - w ds / s
-        newton(false);
         double dzg = -zg - zg * dxg * rxg, dzi = -zi - zi * dxi * rxi, dzo = -zo - zo * dxo * rxo;
         double dzs = has_s ? -zs - zs * dxs * rxs : 0.0, dze = -ze - ze * dxe * rxe, dzp = -zp - zp * dxp * rxp;
         double dzq = -zq - zq * dxq * rxq;
@@ -319,7 +354,7 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
             id = fmax(fmax(fmax(-dzg * rzg, -dzi * rzi), fmax(-dzo * rzo, -dzs * rzs)), fmax(fmax(-dze * rze, -dzp * rzp), -dzq * rzq));
             id = fmax(id, fmax(-dwi * rwi, -dwo * rwo));
         }
-        ip = wmax(ip); id = wmax(id);
+        ip = wmax_pos(ip); id = wmax_pos(id);
         double ap = ip > 1.0 ? 1.0 / ip : 1.0, ad = id > 1.0 ? 1.0 / id : 1.0;
         double mua = 0.0;
         if (act) {
@@ -333,7 +368,9 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
         const double sg = mua / mu;
         smu = sg * sg * sg * mu;
         // ---- corrector
-        newton(true);
+        make_rhs(true, g1, g2);
+        tw_solve<TT>(F, g1, g2, T, lane);
+        recover(g1, g2);
         dzg = (smu - cg) * rxg - zg - zg * dxg * rxg; dzi = (smu - ci) * rxi - zi - zi * dxi * rxi;
         dzo = (smu - co) * rxo - zo - zo * dxo * rxo; dzs = has_s ? (smu - cs) * rxs - zs - zs * dxs * rxs : 0.0;
         dze = (smu - ce) * rxe - ze - ze * dxe * rxe; dzp = (smu - cpp) * rxp - zp - zp * dxp * rxp;
@@ -347,7 +384,7 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
             id = fmax(fmax(fmax(-dzg * rzg, -dzi * rzi), fmax(-dzo * rzo, -dzs * rzs)), fmax(fmax(-dze * rze, -dzp * rzp), -dzq * rzq));
             id = fmax(id, fmax(-dwi * rwi, -dwo * rwo));
         }
-        ip = wmax(ip); id = wmax(id);
+        ip = wmax_pos(ip); id = wmax_pos(id);
         ap = (step_frac * 1.0 < ip) ? step_frac / ip : 1.0;     // min(1, step_frac / ip)
         ad = (step_frac * 1.0 < id) ? step_frac / id : 1.0;
         if (act) {
@@ -362,7 +399,7 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
     if (lane == 0) {
         O.obj[p] = pobj * beta_b * beta_c + kconst;
         O.status[p] = status;
-        O.iters[p] = it;
+        O.iters[p] = it + it0;
     }
     if (O.x_out && act) {
         double *xo_ = O.x_out + p * (long long)O.n;
@@ -377,6 +414,7 @@ __device__ void solve_one(const StageParams &S, const double *cp, const double *
         const int *ri_ = S.row_idx + lane * 4;
         yo_[ri_[0]] = y1 * beta_c; yo_[ri_[1]] = y2 * beta_c; yo_[ri_[2]] = y3 * beta_c; yo_[ri_[3]] = y4 * beta_c;
     }
+    return status == DSP_OPTIMAL ? 0 : it + it0 + 1;
 }
 
 }  // namespace stagewb
