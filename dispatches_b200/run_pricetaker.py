@@ -1,0 +1,84 @@
+"""Batched sweep drivers with the reference's result formats.
+
+Mirrors  case_studies/renewables_case/run_pricetaker_wind_battery.py:37-70 (`run_design`: one JSON per design point,
+skip if the file exists)  and  run_pricetaker_wind_PEM.py:27-110 (`run_design` per (h2_price, pem_ratio), results table
+written with `pd.DataFrame(res).to_csv`).  Where the reference maps `run_design` over a `multiprocessing.Pool`, one
+call here solves every (design point x LMP signal) on the GPU; the files it leaves behind have the same names/keys,
+so downstream readers are untouched.  The horizon is what the GPU templates support (n_time_points <= 32 for the stage
+kernel; the reference's 8736-period full-year LP is not on the GPU path yet -- DESIGN.md §7).
+"""
+from __future__ import annotations
+
+import json
+from itertools import product
+from pathlib import Path
+
+import numpy as np
+
+from . import pricetaker as PT
+
+
+def run_wind_battery_sweep(wind_sizes, battery_ratios, lmp, cf, n_time_points=24, out_dir=None, market="DA",
+                           extant_wind=True):
+    """All design points of run_pricetaker_wind_battery.run_design in one batch.
+
+    lmp [S, >=T] ($/MWh) and cf [>=T] or [S, >=T]: S price signals per design point.  Returns a list of result dicts
+    (one per design point, NPV / annual revenue averaged over the S signals exactly as a caller averaging the
+    reference's per-signal JSONs would) and writes result_<market>_wind_<w>_battery_<r>.json when out_dir is given;
+    existing files are reused (the reference's resume behaviour, :44-54)."""
+    T = int(n_time_points)
+    lmp = np.atleast_2d(np.asarray(lmp, float))[:, :T]
+    cf = np.asarray(cf, float)
+    cf = np.broadcast_to(cf[..., :T], lmp.shape)
+    S = lmp.shape[0]
+    out_dir = Path(out_dir) if out_dir else None
+    designs = list(product(wind_sizes, battery_ratios))
+    todo, results = [], {}
+    for w, r in designs:
+        f = out_dir / f"result_{market}_wind_{w}_battery_{r}.json" if out_dir else None
+        if f is not None and f.exists():
+            results[(w, r)] = json.load(open(f))
+        else:
+            todo.append((w, r))
+    if todo:
+        W = np.repeat([w for w, _ in todo], S)
+        B = np.repeat([w * r for w, r in todo], S)
+        params = {"wind_mw": W, "batt_mw": B, "design_opt": False, "extant_wind": extant_wind,
+                  "wind_resource": np.tile(cf, (len(todo), 1)), "DA_LMPs": np.tile(lmp, (len(todo), 1))}
+        res = PT.wind_battery_optimize(T, params, want_solution=True)
+        npv = res.NPV.reshape(len(todo), S); rev = res.annual_revenue.reshape(len(todo), S)
+        ok = (res.status == 0).reshape(len(todo), S).all(1)
+        for k, (w, r) in enumerate(todo):
+            d = {"wind_mw": float(w), "batt_mw": float(w * r), "NPV": float(npv[k].mean()),
+                 "annual revenue": float(rev[k].mean()), "n_signals": int(S),
+                 "termination_condition": "optimal" if ok[k] else "non-optimal"}
+            results[(w, r)] = d
+            if out_dir:
+                out_dir.mkdir(parents=True, exist_ok=True)
+                json.dump(d, open(out_dir / f"result_{market}_wind_{w}_battery_{r}.json", "w"))
+    return [results[d] for d in designs]
+
+
+def run_wind_pem_sweep(h2_prices, pem_ratios, lmp, cf, wind_mw=847.0, n_time_points=24, csv_path=None):
+    """run_pricetaker_wind_PEM.py:100-110 for fixed PEM sizes (design_opt False, batt_mw = 0): the table with the
+    reference's columns wind_mw, batt_mw, pem_mw, h2_price_per_kg, annual_rev_h2, annual_rev_E, NPV."""
+    T = int(n_time_points)
+    lmp = np.atleast_2d(np.asarray(lmp, float))[:, :T]
+    S = lmp.shape[0]
+    cf = np.broadcast_to(np.asarray(cf, float)[..., :T], lmp.shape)
+    designs = [(h, p) for h, p in product(h2_prices, pem_ratios) if p is not None and p > 0]
+    D = len(designs)
+    params = {"wind_mw": wind_mw, "batt_mw": 0.0, "pem_mw": np.repeat([p * wind_mw for _, p in designs], S),
+              "h2_price_per_kg": np.repeat([h for h, _ in designs], S), "design_opt": False, "extant_wind": True,
+              "wind_resource": np.tile(cf, (D, 1)), "DA_LMPs": np.tile(lmp, (D, 1))}
+    res = PT.wind_battery_pem_optimize(T, params, want_solution=True)
+    rows = []
+    for k, (h, p) in enumerate(designs):
+        sl = slice(k * S, (k + 1) * S)
+        rows.append({"wind_mw": wind_mw, "batt_mw": 0.0, "pem_mw": p * wind_mw, "h2_price_per_kg": h,
+                     "annual_rev_h2": float(res.annual_rev_h2[sl].mean()), "annual_rev_E": float(res.annual_elec_revenue[sl].mean()),
+                     "NPV": float(res.NPV[sl].mean())})
+    if csv_path:
+        import pandas as pd
+        pd.DataFrame(rows).to_csv(csv_path)
+    return rows

@@ -235,3 +235,20 @@ def test_reference_shaped_api():
     assert len(soc) == 24 and soc[-1] == 0.0 and wcap == pytest.approx(W) and npv == pytest.approx(res.NPV[0])
     with pytest.raises(NotImplementedError):
         PT.wind_battery_optimize(24, dict(params, design_opt=True))
+
+
+def test_sweep_drivers_write_reference_shaped_results(tmp_path):
+    """run_design-style sweep: JSON per design point (resume on rerun) and the wind+PEM results table."""
+    from dispatches_b200 import run_pricetaker as RP
+    lmp, cf, W, P = SC.c2(6)
+    out = RP.run_wind_battery_sweep([400.0, 847.0], [0.1, 0.25], lmp, cf, out_dir=tmp_path)
+    assert len(out) == 4 and (tmp_path / "result_DA_wind_847.0_battery_0.25.json").exists()
+    ref = np.mean([-H.solve(L.wind_battery_raw(l, cf, 847.0, 0.25 * 847.0))[0] * 1e5 for l in lmp])
+    assert out[3]["NPV"] == pytest.approx(ref, rel=1e-6)
+    n0 = S.launch_count()
+    again = RP.run_wind_battery_sweep([400.0, 847.0], [0.1, 0.25], lmp, cf, out_dir=tmp_path)
+    assert S.launch_count() == n0 and again == out                       # everything came from the JSON cache
+    rows = RP.run_wind_pem_sweep([2.0, 2.5], [0.25, 0.5], lmp, cf, csv_path=tmp_path / "wind_PEM.csv")
+    lp = L.wind_battery_raw(lmp[0], cf, 847.0, 0.0, pem_mw=0.25 * 847.0, h2_price=2.0)
+    npv = np.mean([-H.solve(L.wind_battery_raw(l, cf, 847.0, 0.0, pem_mw=0.25 * 847.0, h2_price=2.0))[0] * 1e5 for l in lmp])
+    assert rows[0]["NPV"] == pytest.approx(npv, rel=1e-6) and (tmp_path / "wind_PEM.csv").exists()
