@@ -32,9 +32,7 @@
 namespace {
 
 constexpr int kMaxWarps = 16;
-constexpr int kMaxPairPasses = 4;          // w*w <= 128  ->  w <= 11 on the fast path
 constexpr double kGapFloor = 1e-4;         // scaled-objective floor of the relative gap test
-constexpr double kPivotRel = 1e-14;
 
 struct KParams {
     // template
@@ -128,95 +126,89 @@ __device__ __forceinline__ Hot hot_views(const unsigned char *base, const KParam
     return h;
 }
 
-// ---- band LDL' of M (lower band, row-major Mb[i*(w+1)+k] = M[i][i-k]); on exit the diagonal slot holds
-// ---- 1/d_i (0 for a dropped pivot) and the off-diagonal slots the UNSCALED column entries L[i][i-k]*d_{i-k}.
-// ---- diag0[i] = M[i][i] before elimination (pivot test).  One warp.
-__device__ void band_factor(double *Mb, const double *diag0, int m, int w, int lane) {
-    const int W1 = w + 1;
-    const int npairs = w * w;
-    int pr[kMaxPairPasses], pq[kMaxPairPasses];
+__device__ __forceinline__ double dmaxd(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double frcpd(double x) {          // reciprocal: MUFU seed + 2 Newton steps (no IEEE division)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+// ---- band LDL' of M.  Lower band, row-major, W1 = W+1 slots per row: Mb[i*W1+k] = M[i][i-k]; the array carries W
+// ---- zero rows in front and behind (no bounds checks in the sweeps).  On exit the diagonal slot holds 1/d_i (0 for a
+// ---- non-positive pivot) and the off-diagonal slots the UNSCALED column entries L[i][i-k]*d_{i-k}.  One warp.
+template <int W>
+__device__ __forceinline__ void band_factor(double *Mb, int m, int lane) {
+    constexpr int W1 = W + 1, NP = W * W, PASSES = (NP + 31) / 32;
+    int off_lr[PASSES], off_lq[PASSES], off_t[PASSES];
 #pragma unroll
-    for (int ps = 0; ps < kMaxPairPasses; ++ps) {
-        int idx = lane + 32 * ps;
-        int r = 1 + idx / max(w, 1), q = 1 + idx % max(w, 1);
-        bool ok = (idx < npairs) && (q <= r);
-        pr[ps] = ok ? r : 0;
-        pq[ps] = ok ? q : 0;
+    for (int ps = 0; ps < PASSES; ++ps) {
+        const int idx = lane + 32 * ps;
+        const int r = 1 + idx / W, q = 1 + idx % W;
+        const bool ok = (idx < NP) && (q <= r);
+        off_lr[ps] = ok ? r * W1 + r : -1;
+        off_lq[ps] = q * W1 + q;
+        off_t[ps] = r * W1 + (r - q);
     }
     for (int j = 0; j < m; ++j) {
-        const double piv = Mb[j * W1];
-        const double inv = (piv > kPivotRel * diag0[j]) ? 1.0 / piv : 0.0;
-        const int rmax = min(w, m - 1 - j);
-        if (npairs <= 32 * kMaxPairPasses) {
+        double *row = Mb + j * W1;
+        const double piv = row[0];
+        const double inv = piv > 0.0 ? frcpd(piv) : 0.0;
 #pragma unroll
-            for (int ps = 0; ps < kMaxPairPasses; ++ps) {
-                const int r = pr[ps], q = pq[ps];
-                if (r != 0 && r <= rmax) {
-                    const double lr = Mb[(j + r) * W1 + r];
-                    const double lq = Mb[(j + q) * W1 + q];
-                    Mb[(j + r) * W1 + (r - q)] -= lr * lq * inv;
-                }
-            }
-        } else {
-            for (int idx = lane; idx < npairs; idx += 32) {
-                const int r = 1 + idx / w, q = 1 + idx % w;
-                if (q <= r && r <= rmax) {
-                    const double lr = Mb[(j + r) * W1 + r];
-                    const double lq = Mb[(j + q) * W1 + q];
-                    Mb[(j + r) * W1 + (r - q)] -= lr * lq * inv;
-                }
-            }
+        for (int ps = 0; ps < PASSES; ++ps) {
+            if (off_lr[ps] >= 0) row[off_t[ps]] -= row[off_lr[ps]] * row[off_lq[ps]] * inv;
         }
         __syncwarp();
-        if (lane == 0) Mb[j * W1] = inv;
+        if (lane == 0) row[0] = inv;
     }
     __syncwarp();
 }
 
-// ---- solve M v = r in place with the factor produced by band_factor.  One warp.
-__device__ void band_solve(const double *Mb, double *v, int m, int w, int lane) {
-    const int W1 = w + 1;
-    // forward: L t = r     (column sweeps, lanes over the w sub-diagonal entries)
-    for (int j = 0; j < m; ++j) {
+// ---- solve M v = r in place (v carries W padding entries in front and behind).  One warp.
+template <int W>
+__device__ __forceinline__ void band_solve(const double *Mb, double *v, int m, int lane) {
+    constexpr int W1 = W + 1;
+    const int r = (lane % W) + 1;                 // lanes >= W idle in the sweeps (W <= 16 < 32)
+    const bool on = lane < W;
+    for (int j = 0; j < m; ++j) {                 // forward: L t = r  (column sweeps)
         const double t = v[j] * Mb[j * W1];
-        for (int r = lane + 1; r <= w; r += 32)
-            if (j + r < m) v[j + r] -= Mb[(j + r) * W1 + r] * t;
+        if (on) v[j + r] -= Mb[(j + r) * W1 + r] * t;
         __syncwarp();
     }
-    // t' = D^-1 t
-    for (int j = lane; j < m; j += 32) v[j] *= Mb[j * W1];
+    for (int j = lane; j < m; j += 32) v[j] *= Mb[j * W1];      // t' = D^-1 t
     __syncwarp();
-    // backward: L' v = t'
-    for (int i = m - 1; i > 0; --i) {
+    for (int i = m - 1; i > 0; --i) {             // backward: L' v = t'
         const double vi = v[i];
-        for (int r = lane + 1; r <= w; r += 32)
-            if (i - r >= 0) v[i - r] -= Mb[(i - r) * W1] * Mb[i * W1 + r] * vi;
+        if (on) v[i - r] -= Mb[(i - r) * W1] * Mb[i * W1 + r] * vi;
         __syncwarp();
     }
 }
 
 struct Work {   // per-warp shared-memory vectors
-    double *x, *z, *c, *rd, *d, *dx, *cor;     // n
-    double *s, *wv, *u, *ru, *cors;            // nb
-    double *y, *b, *rp, *dy;                   // m
-    double *Mb;                                // m*(w+1)
+    double *x, *z, *c, *rd, *d, *dx, *cor, *rx;     // n
+    double *s, *wv, *u, *ru, *cors, *rs;            // nb
+    double *y, *b, *rp;                             // m
+    double *dy;                                     // m + 2W (padded)
+    double *Mb;                                     // (m + 2W) * (W+1) (padded)
 };
 
 // Newton direction for the complementarity targets  x z -> ax,  s w -> as  (ax = as = 0: affine predictor;
 // ax_j = smu - cor_j: centring corrector).  On exit W.dx = dx, W.dy = dy.
-template <bool CORR>
+template <bool CORR, int BW>
 __device__ __forceinline__ void newton(const Work &W, const Hot &H, const KParams &P, double smu, int lane) {
     const int n = P.n, nb = P.nb, m = P.m;
-    for (int j = lane; j < n; j += 32) {
-        const double xj = W.x[j], zj = W.z[j];
-        double h = W.rd[j] + zj;
-        if (CORR) h -= (smu - W.cor[j]) / xj;
-        if (j < nb) {
-            const double sj = W.s[j], wj = W.wv[j];
-            double as = -wj * W.ru[j];
-            if (CORR) as += smu - W.cors[j];
-            h += as / sj - wj;
-        }
+    for (int j = lane; j < nb; j += 32) {           // bounded columns
+        const double wj = W.wv[j];
+        double h = W.rd[j] + W.z[j], as = -wj * W.ru[j];
+        if (CORR) { h -= (smu - W.cor[j]) * W.rx[j]; as += smu - W.cors[j]; }
+        h += as * W.rs[j] - wj;
+        W.dx[j] = W.d[j] * h;
+    }
+    for (int j = nb + lane; j < n; j += 32) {       // the rest
+        double h = W.rd[j] + W.z[j];
+        if (CORR) h -= (smu - W.cor[j]) * W.rx[j];
         W.dx[j] = W.d[j] * h;
     }
     __syncwarp();
@@ -226,7 +218,7 @@ __device__ __forceinline__ void newton(const Work &W, const Hot &H, const KParam
         W.dy[i] = acc;
     }
     __syncwarp();
-    band_solve(W.Mb, W.dy, m, P.w, lane);
+    band_solve<BW>(W.Mb, W.dy, m, lane);
     for (int j = lane; j < n; j += 32) {
         double acc = 0.0;
         for (int q = H.At_ptr[j]; q < H.At_ptr[j + 1]; ++q) acc += H.At_val[q] * W.dy[H.At_idx[q]];
@@ -235,10 +227,33 @@ __device__ __forceinline__ void newton(const Work &W, const Hot &H, const KParam
     __syncwarp();
 }
 
-__device__ __forceinline__ double ratio(double v, double dv) { return dv < 0.0 ? -v / dv : 1e300; }
+// step-length pass shared by predictor and corrector: 1/alpha_p, 1/alpha_d candidates of this lane
+template <bool CORR>
+__device__ __forceinline__ void step_pass(const Work &W, const KParams &P, double smu, int lane, double &ip, double &id) {
+    const int n = P.n, nb = P.nb;
+    for (int j = lane; j < nb; j += 32) {
+        const double zj = W.z[j], wj = W.wv[j], rxj = W.rx[j], rsj = W.rs[j], dxj = W.dx[j];
+        double dzj = -zj - zj * dxj * rxj;
+        const double dsj = W.ru[j] - dxj;
+        double dwj = -wj - wj * dsj * rsj;
+        if (CORR) { dzj += (smu - W.cor[j]) * rxj; dwj += (smu - W.cors[j]) * rsj; }
+        ip = dmaxd(ip, dmaxd(-dxj * rxj, -dsj * rsj));
+        id = dmaxd(id, dmaxd(-dzj * frcpd(zj), -dwj * frcpd(wj)));
+    }
+    for (int j = nb + lane; j < n; j += 32) {
+        const double zj = W.z[j], rxj = W.rx[j], dxj = W.dx[j];
+        double dzj = -zj - zj * dxj * rxj;
+        if (CORR) dzj += (smu - W.cor[j]) * rxj;
+        ip = dmaxd(ip, -dxj * rxj);
+        id = dmaxd(id, -dzj * frcpd(zj));
+    }
+}
 
-__device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long long p, int lane) {
-    const int n = P.n, nb = P.nb, m = P.m, w = P.w;
+template <int BW>
+__device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long long p, int lane, double step_frac,
+                          double reg, int it0, int *status_out, int *iters_out) {
+    const int n = P.n, nb = P.nb, m = P.m;
+    constexpr int W1 = BW + 1;
     const double *cp = P.cparams + p * (long long)P.Pc;
     const double *rp_ = P.rparams + p * P.rstride;
     // ---- instantiate c, b, u, objective constant from the parameter maps
@@ -247,19 +262,19 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
         double acc = P.c0[j];
         for (int q = P.cm_ptr[j]; q < P.cm_ptr[j + 1]; ++q) acc += P.cm_val[q] * cp[P.cm_idx[q]];
         W.c[j] = acc;
-        cmax = fmax(cmax, fabs(acc));
+        cmax = dmaxd(cmax, fabs(acc));
     }
     for (int i = lane; i < m; i += 32) {
         double acc = P.b0[i];
         for (int q = P.bm_ptr[i]; q < P.bm_ptr[i + 1]; ++q) acc += P.bm_val[q] * rp_[P.bm_idx[q]];
         W.b[i] = acc;
-        bmax = fmax(bmax, fabs(acc));
+        bmax = dmaxd(bmax, fabs(acc));
     }
     for (int j = lane; j < nb; j += 32) {
         double acc = P.u0[j];
         for (int q = P.um_ptr[j]; q < P.um_ptr[j + 1]; ++q) acc += P.um_val[q] * rp_[P.um_idx[q]];
         W.u[j] = acc;
-        bmax = fmax(bmax, acc);
+        bmax = dmaxd(bmax, acc);
     }
     for (int r = lane; r < P.Pr; r += 32) kconst += P.omap[r] * rp_[r];
     for (int r = lane; r < P.Pc; r += 32) kconst += P.ocmap[r] * cp[r];
@@ -268,19 +283,19 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
     bmax = warp_max(bmax);
     const double beta_b = bmax > 0.0 ? bmax : 1.0;
     const double beta_c = cmax > 0.0 ? cmax : 1.0;
-    // ---- scale, start point
+    // ---- scale, start point, zero the paddings
     double bsmax = 0.0;
     for (int i = lane; i < m; i += 32) {
         const double v = W.b[i] / beta_b;
         W.b[i] = v;
         W.y[i] = 0.0;
-        bsmax = fmax(bsmax, fabs(v));
+        bsmax = dmaxd(bsmax, fabs(v));
     }
     for (int j = lane; j < n; j += 32) {
         W.c[j] = W.c[j] / beta_c;
         double xj = 1.0;
         if (j < nb) {
-            const double uj = fmax(W.u[j] / beta_b, 1e-10);
+            const double uj = dmaxd(W.u[j] / beta_b, 1e-10);
             W.u[j] = uj;
             xj = fmin(1.0, 0.5 * uj);
             W.s[j] = uj - xj;
@@ -289,6 +304,8 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
         W.x[j] = xj;
         W.z[j] = 1.0;
     }
+    for (int k = lane; k < BW * W1; k += 32) { W.Mb[-(k + 1)] = 0.0; W.Mb[m * W1 + k] = 0.0; }
+    for (int k = lane; k < BW; k += 32) { W.dy[-(k + 1)] = 0.0; W.dy[m + k] = 0.0; }
     bsmax = warp_max(bsmax);
     const double nrm_b = 1.0 + bsmax, nrm_c = 1.0 + (cmax > 0.0 ? 1.0 : 0.0);
     const double ntot = (double)(n + nb);
@@ -297,33 +314,37 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
     int status = DSP_MAX_ITER, it = 0;
     double pobj = 0.0;
     for (it = 0; it <= P.max_iter; ++it) {
-        // ---- residuals, complementarity, objectives
+        // ---- residuals, complementarity, objectives, scaling matrix (reciprocals kept for the whole iteration)
         double pmax = 0.0, dmax = 0.0, musum = 0.0, po = 0.0, dobj = 0.0;
         for (int i = lane; i < m; i += 32) {
             double acc = W.b[i];
             for (int q = H.A_ptr[i]; q < H.A_ptr[i + 1]; ++q) acc -= H.A_val[q] * W.x[H.A_idx[q]];
             W.rp[i] = acc;
-            pmax = fmax(pmax, fabs(acc));
+            pmax = dmaxd(pmax, fabs(acc));
             dobj += W.b[i] * W.y[i];
         }
         for (int j = lane; j < n; j += 32) {
             const double xj = W.x[j], zj = W.z[j];
             double acc = W.c[j] - zj;
             for (int q = H.At_ptr[j]; q < H.At_ptr[j + 1]; ++q) acc -= H.At_val[q] * W.y[H.At_idx[q]];
-            double t = zj / xj;
+            const double rxj = frcpd(xj);
+            double t = zj * rxj + reg;
             if (j < nb) {
                 const double sj = W.s[j], wj = W.wv[j], uj = W.u[j];
                 acc += wj;
                 const double r = uj - xj - sj;
+                const double rsj = frcpd(sj);
                 W.ru[j] = r;
-                pmax = fmax(pmax, fabs(r));
+                W.rs[j] = rsj;
+                pmax = dmaxd(pmax, fabs(r));
                 musum += sj * wj;
                 dobj -= uj * wj;
-                t += wj / sj;
+                t += wj * rsj;
             }
+            W.rx[j] = rxj;
             W.rd[j] = acc;
-            W.d[j] = 1.0 / (t + P.reg);
-            dmax = fmax(dmax, fabs(acc));
+            W.d[j] = frcpd(t);
+            dmax = dmaxd(dmax, fabs(acc));
             musum += xj * zj;
             po += W.c[j] * xj;
         }
@@ -334,10 +355,10 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
         dobj = warp_sum(dobj);
         pobj = po;
         const double mu = musum / ntot;
-        const double gap = fabs(po - dobj) / fmax(kGapFloor, fabs(po));
+        const double gap = fabs(po - dobj) / dmaxd(kGapFloor, fabs(po));
         if (!(mu == mu) || !(po == po) || mu > 1e100) { status = DSP_NUMERICAL; break; }
-        const double res = fmax(pmax / nrm_b, dmax / nrm_c);
-        const double cgap = ntot * mu / fmax(kGapFloor, fabs(po));   // what further iterations can still reduce
+        const double res = dmaxd(pmax / nrm_b, dmax / nrm_c);
+        const double cgap = ntot * mu / dmaxd(kGapFloor, fabs(po));   // what further iterations can still reduce
         if (res < P.feas_tol && gap < P.tol) { status = DSP_OPTIMAL; break; }
         // complementarity has converged but residuals / objective gap sit at the rounding floor of the
         // ill-conditioned normal equations: iterating further only loses accuracy -> accept what is there
@@ -349,44 +370,30 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
         if (it == P.max_iter) break;
         __syncwarp();
         // ---- assemble the band of M = A D A'
-        const int nent = m * (w + 1);
+        const int nent = m * W1;
         for (int e = lane; e < nent; e += 32) {
             double acc = 0.0;
             for (int q = H.asm_ptr[e]; q < H.asm_ptr[e + 1]; ++q) acc += H.asm_val[q] * W.d[H.asm_col[q]];
             W.Mb[e] = acc;
         }
         __syncwarp();
-        for (int i = lane; i < m; i += 32) W.dy[i] = W.Mb[i * (w + 1)];
-        __syncwarp();
-        band_factor(W.Mb, W.dy, m, w, lane);
+        band_factor<BW>(W.Mb, m, lane);
         // ---- affine predictor
-        newton<false>(W, H, P, 0.0, lane);
-        double ap = 1e300, ad = 1e300;
-        for (int j = lane; j < n; j += 32) {
-            const double xj = W.x[j], zj = W.z[j], dxj = W.dx[j];
-            const double dzj = -zj - zj * dxj / xj;
-            ap = fmin(ap, ratio(xj, dxj));
-            ad = fmin(ad, ratio(zj, dzj));
-            if (j < nb) {
-                const double sj = W.s[j], wj = W.wv[j];
-                const double dsj = W.ru[j] - dxj;
-                const double dwj = -wj - wj * dsj / sj;
-                ap = fmin(ap, ratio(sj, dsj));
-                ad = fmin(ad, ratio(wj, dwj));
-            }
-        }
-        ap = fmin(1.0, warp_min(ap));
-        ad = fmin(1.0, warp_min(ad));
+        newton<false, BW>(W, H, P, 0.0, lane);
+        double ip = 0.0, id = 0.0;
+        step_pass<false>(W, P, 0.0, lane, ip, id);
+        ip = warp_max(ip); id = warp_max(id);
+        double ap = ip > 1.0 ? 1.0 / ip : 1.0, ad = id > 1.0 ? 1.0 / id : 1.0;
         double mua = 0.0;
         for (int j = lane; j < n; j += 32) {
             const double xj = W.x[j], zj = W.z[j], dxj = W.dx[j];
-            const double dzj = -zj - zj * dxj / xj;
+            const double dzj = -zj - zj * dxj * W.rx[j];
             mua += (xj + ap * dxj) * (zj + ad * dzj);
             W.cor[j] = dxj * dzj;
             if (j < nb) {
                 const double sj = W.s[j], wj = W.wv[j];
                 const double dsj = W.ru[j] - dxj;
-                const double dwj = -wj - wj * dsj / sj;
+                const double dwj = -wj - wj * dsj * W.rs[j];
                 mua += (sj + ap * dsj) * (wj + ad * dwj);
                 W.cors[j] = dsj * dwj;
             }
@@ -396,30 +403,19 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
         const double smu = sg * sg * sg * mu;
         __syncwarp();
         // ---- centring corrector
-        newton<true>(W, H, P, smu, lane);
-        ap = 1e300; ad = 1e300;
+        newton<true, BW>(W, H, P, smu, lane);
+        ip = 0.0; id = 0.0;
+        step_pass<true>(W, P, smu, lane, ip, id);
+        ip = warp_max(ip); id = warp_max(id);
+        ap = step_frac < ip ? step_frac / ip : 1.0;
+        ad = step_frac < id ? step_frac / id : 1.0;
         for (int j = lane; j < n; j += 32) {
-            const double xj = W.x[j], zj = W.z[j], dxj = W.dx[j];
-            const double dzj = (smu - W.cor[j]) / xj - zj - zj * dxj / xj;
-            ap = fmin(ap, ratio(xj, dxj));
-            ad = fmin(ad, ratio(zj, dzj));
+            const double xj = W.x[j], zj = W.z[j], dxj = W.dx[j], rxj = W.rx[j];
+            const double dzj = (smu - W.cor[j]) * rxj - zj - zj * dxj * rxj;
             if (j < nb) {
-                const double sj = W.s[j], wj = W.wv[j];
+                const double sj = W.s[j], wj = W.wv[j], rsj = W.rs[j];
                 const double dsj = W.ru[j] - dxj;
-                const double dwj = (smu - W.cors[j]) / sj - wj - wj * dsj / sj;
-                ap = fmin(ap, ratio(sj, dsj));
-                ad = fmin(ad, ratio(wj, dwj));
-            }
-        }
-        ap = fmin(1.0, P.step_frac * warp_min(ap));
-        ad = fmin(1.0, P.step_frac * warp_min(ad));
-        for (int j = lane; j < n; j += 32) {
-            const double xj = W.x[j], zj = W.z[j], dxj = W.dx[j];
-            const double dzj = (smu - W.cor[j]) / xj - zj - zj * dxj / xj;
-            if (j < nb) {
-                const double sj = W.s[j], wj = W.wv[j];
-                const double dsj = W.ru[j] - dxj;
-                const double dwj = (smu - W.cors[j]) / sj - wj - wj * dsj / sj;
+                const double dwj = (smu - W.cors[j]) * rsj - wj - wj * dsj * rsj;
                 W.s[j] = sj + ap * dsj;
                 W.wv[j] = wj + ad * dwj;
             }
@@ -433,7 +429,7 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
     if (lane == 0) {
         P.obj[p] = pobj * beta_b * beta_c + kconst;
         P.status[p] = status;
-        P.iters[p] = it;
+        P.iters[p] = it + it0;
     }
     if (P.x_out) {
         double *xo = P.x_out + p * (long long)n;
@@ -444,8 +440,11 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
         for (int i = lane; i < m; i += 32) yo[i] = W.y[i] * beta_c;
     }
     __syncwarp();
+    *status_out = status;
+    *iters_out = it + it0;
 }
 
+template <int BW>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) dsp_ipm_band_kernel(const KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -458,16 +457,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) dsp_ipm_band_kernel(const K
     double *base = (double *)(smem + P.prob_off) + (size_t)warp * P.prob_doubles;
     Work W;
     const int n = P.n, nb = P.nb, m = P.m;
-    W.x = base; W.z = W.x + n; W.c = W.z + n; W.rd = W.c + n; W.d = W.rd + n; W.dx = W.d + n; W.cor = W.dx + n;
-    W.s = W.cor + n; W.wv = W.s + nb; W.u = W.wv + nb; W.ru = W.u + nb; W.cors = W.ru + nb;
-    W.y = W.cors + nb; W.b = W.y + m; W.rp = W.b + m; W.dy = W.rp + m;
-    W.Mb = W.dy + m;
+    W.x = base; W.z = W.x + n; W.c = W.z + n; W.rd = W.c + n; W.d = W.rd + n; W.dx = W.d + n; W.cor = W.dx + n; W.rx = W.cor + n;
+    W.s = W.rx + n; W.wv = W.s + nb; W.u = W.wv + nb; W.ru = W.u + nb; W.cors = W.ru + nb; W.rs = W.cors + nb;
+    W.y = W.rs + nb; W.b = W.y + m; W.rp = W.b + m;
+    W.dy = W.rp + m + BW;
+    W.Mb = W.dy + m + BW + BW * (BW + 1);
     for (;;) {
         unsigned long long t = 0;
         if (lane == 0) t = atomicAdd(P.ticket, 1ULL);
         t = __shfl_sync(0xffffffffu, t, 0);
         if ((long long)t >= P.N) break;
-        solve_one(W, H, P, (long long)t, lane);
+        int st, it0 = 0;
+        // second attempt (shorter step, stronger proximal term) for the rare LP whose first attempt ends non-optimal
+        solve_one<BW>(W, H, P, (long long)t, lane, P.step_frac, P.reg, 0, &st, &it0);
+        if (st != DSP_OPTIMAL) solve_one<BW>(W, H, P, (long long)t, lane, 0.99, 10.0 * P.reg, it0, &st, &it0);
     }
 }
 
@@ -593,8 +596,18 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     }
     const int m = D->m, n = D->n, nb = D->nb, w = D->w;
     const int nnz = D->A_ptr[m];
-    const int nent = m * (w + 1);
-    const int nasm = D->asm_ptr[nent];
+    // the kernels are instantiated for half bandwidths 1, 2, 4, 8, 16: pad the band storage to the next one
+    int wt = 1;
+    while (wt < w) wt *= 2;
+    if (wt > 16) { g_err = "dsp_lp_template_create: half bandwidth of A*A' above 16 is not supported"; return DSP_E_ARG; }
+    const int nent = m * (wt + 1);
+    const int nasm = D->asm_ptr[m * (w + 1)];
+    std::vector<int> asm_ptr_pad(nent + 1, 0);
+    for (int i = 0; i < m; ++i)
+        for (int k = 0; k <= wt; ++k) {
+            const int cnt = (k <= w) ? D->asm_ptr[i * (w + 1) + k + 1] - D->asm_ptr[i * (w + 1) + k] : 0;
+            asm_ptr_pad[i * (wt + 1) + k + 1] = asm_ptr_pad[i * (wt + 1) + k] + cnt;
+        }
     // CSC of A
     std::vector<int> At_ptr(n + 1, 0), At_idx(nnz);
     std::vector<double> At_val(nnz);
@@ -628,7 +641,7 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
         memcpy(pi, D->A_idx, (size_t)nnz * 4); pi += nnz;
         memcpy(pi, At_ptr.data(), (size_t)(n + 1) * 4); pi += n + 1;
         memcpy(pi, At_idx.data(), (size_t)nnz * 4); pi += nnz;
-        memcpy(pi, D->asm_ptr, (size_t)(nent + 1) * 4); pi += nent + 1;
+        memcpy(pi, asm_ptr_pad.data(), (size_t)(nent + 1) * 4); pi += nent + 1;
         memcpy(pi, D->asm_col, (size_t)nasm * 4);
     }
     dsp_template *T = new dsp_template();
@@ -644,7 +657,7 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     T->sm_count = prop.multiProcessorCount;
     T->smem_optin = (int)prop.sharedMemPerBlockOptin;
     KParams &K = T->kp;
-    K.m = m; K.n = n; K.nb = nb; K.w = w; K.Pc = D->Pc; K.Pr = D->Pr; K.nnz = nnz; K.nasm = nasm;
+    K.m = m; K.n = n; K.nb = nb; K.w = wt; K.Pc = D->Pc; K.Pr = D->Pr; K.nnz = nnz; K.nasm = nasm;
     K.hot_bytes = (int)hot_bytes;
     K.o0 = D->o0;
     auto up_d = [&](const double *src, size_t cnt, const double **dst) -> int {
@@ -690,8 +703,12 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     if (rc) return DSP_E_CUDA;
     CK(cudaMalloc((void **)&T->ticket, 16 * sizeof(unsigned long long)));
     T->dev_allocs.push_back(T->ticket);
-    K.prob_doubles = 7 * n + 5 * nb + 4 * m + m * (w + 1);
-    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    K.prob_doubles = 8 * n + 6 * nb + 3 * m + (m + 2 * wt) + (m + 2 * wt) * (wt + 1);
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaStreamCreateWithFlags(&T->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&T->stream2, cudaStreamNonBlocking));
     *out = T;
@@ -795,7 +812,13 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
     K.prob_off = (int)off;
     const size_t smem = off + (size_t)warps * prob_bytes;
     CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
-    dsp_ipm_band_kernel<<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+    switch (K.w) {
+        case 1: dsp_ipm_band_kernel<1><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K); break;
+        case 2: dsp_ipm_band_kernel<2><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K); break;
+        case 4: dsp_ipm_band_kernel<4><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K); break;
+        case 8: dsp_ipm_band_kernel<8><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K); break;
+        default: dsp_ipm_band_kernel<16><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K); break;
+    }
     CK(cudaGetLastError());
     {
         std::lock_guard<std::mutex> lk(g_mu);
