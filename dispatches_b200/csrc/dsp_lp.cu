@@ -31,6 +31,15 @@
 
 namespace {
 
+#ifdef DSP_PHASES            // developer instrumentation: per-phase cycle counters (warp 0 of block 0 accumulates)
+__device__ unsigned long long g_phase[16];
+#define PH_INIT long long ph_t0 = clock64();
+#define PH(k) do { long long ph_t1 = clock64(); if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_phase[k], (unsigned long long)(ph_t1 - ph_t0)); ph_t0 = clock64(); } while (0)
+#else
+#define PH_INIT
+#define PH(k)
+#endif
+
 constexpr int kMaxWarps = 16;
 constexpr double kGapFloor = 1e-4;         // scaled-objective floor of the relative gap test
 
@@ -313,7 +322,9 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
 
     int status = DSP_MAX_ITER, it = 0;
     double pobj = 0.0;
+    PH_INIT
     for (it = 0; it <= P.max_iter; ++it) {
+        PH(7);
         // ---- residuals, complementarity, objectives, scaling matrix (reciprocals kept for the whole iteration)
         double pmax = 0.0, dmax = 0.0, musum = 0.0, po = 0.0, dobj = 0.0;
         for (int i = lane; i < m; i += 32) {
@@ -369,6 +380,7 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
         }
         if (it == P.max_iter) break;
         __syncwarp();
+        PH(0);
         // ---- assemble the band of M = A D A'
         const int nent = m * W1;
         for (int e = lane; e < nent; e += 32) {
@@ -377,9 +389,12 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
             W.Mb[e] = acc;
         }
         __syncwarp();
+        PH(1);
         band_factor<BW>(W.Mb, m, lane);
+        PH(2);
         // ---- affine predictor
         newton<false, BW>(W, H, P, 0.0, lane);
+        PH(3);
         double ip = 0.0, id = 0.0;
         step_pass<false>(W, P, 0.0, lane, ip, id);
         ip = warp_max(ip); id = warp_max(id);
@@ -402,8 +417,10 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
         const double sg = mua / mu;
         const double smu = sg * sg * sg * mu;
         __syncwarp();
+        PH(4);
         // ---- centring corrector
         newton<true, BW>(W, H, P, smu, lane);
+        PH(5);
         ip = 0.0; id = 0.0;
         step_pass<true>(W, P, smu, lane, ip, id);
         ip = warp_max(ip); id = warp_max(id);
@@ -424,6 +441,7 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
         }
         for (int i = lane; i < m; i += 32) W.y[i] += ad * W.dy[i];
         __syncwarp();
+        PH(6);
     }
     // ---- results
     if (lane == 0) {
@@ -569,6 +587,13 @@ struct dsp_template {
 extern "C" {
 
 const char *dsp_lp_version(void) { return DSP_VERSION; }
+#ifdef DSP_PHASES
+int dsp_lp_phases(unsigned long long *out16, int reset) {
+    cudaMemcpyFromSymbol(out16, g_phase, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase, z, sizeof(z)); }
+    return 0;
+}
+#endif
 const char *dsp_lp_last_error(void) { return g_err.c_str(); }
 int64_t dsp_lp_launch_count(void) { return g_launches; }
 int dsp_lp_last_launch(int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *ppc) {

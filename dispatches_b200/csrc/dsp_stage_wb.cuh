@@ -194,7 +194,9 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
 
     int status = DSP_MAX_ITER, it = 0;
     double pobj = 0.0;
+    PH_INIT
     for (it = 0; it <= max_iter; ++it) {
+        PH(15);
         // ---- residuals
         const double xs_p = up1(xs, lane), xe_p = up1(xe, lane);
         const double y1n = down1(y1, lane), y2n = down1(y2, lane);
@@ -233,6 +235,7 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
             break;
         }
         if (it == max_iter) break;
+        PH(8);
         // ---- scaling matrix D and reciprocals
         const double rxg = frcp(xg), rxi = frcp(xi), rxo = frcp(xo), rxe = frcp(xe), rxp = frcp(xp), rxq = frcp(xq);
         const double rxs = has_s ? frcp(xs) : 0.0;
@@ -304,8 +307,10 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
         };
         // ---- twisted block LDL'; the forward elimination of the PREDICTOR right-hand side rides along in the same
         // ---- sweep (its shuffles and FMAs fill the latency shadow of the 2x2 inversions)
+        PH(9);
         double g1, g2;
         make_rhs(false, g1, g2);
+        PH(10);
         Sym2 Dh = D;
         F.Dhinv = inv_spd(Dh);
         F.G.a = F.G.b = F.G.c = F.G.d = 0.0;
@@ -341,8 +346,10 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
                 F.Dhinv = inv_spd(Dh);
             }
         }
+        PH(11);
         // ---- affine predictor: backward sweep only
         tw_back<TT>(F, g1, g2, T, lane);
+        PH(12);
         recover(g1, g2);
         // dz = ax/x - z - z dx / x ;  dw = as/s - w - w ds / s
         double dzg = -zg - zg * dxg * rxg, dzi = -zi - zi * dxi * rxi, dzo = -zo - zo * dxo * rxo;
@@ -370,9 +377,11 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
         csi = dsi * dwi; cso = dso * dwo;
         const double sg = mua / mu;
         smu = sg * sg * sg * mu;
+        PH(13);
         // ---- corrector
         make_rhs(true, g1, g2);
         tw_solve<TT>(F, g1, g2, T, lane);
+        PH(14);
         recover(g1, g2);
         dzg = (smu - cg) * rxg - zg - zg * dxg * rxg; dzi = (smu - ci) * rxi - zi - zi * dxi * rxi;
         dzo = (smu - co) * rxo - zo - zo * dxo * rxo; dzs = has_s ? (smu - cs) * rxs - zs - zs * dxs * rxs : 0.0;
