@@ -252,3 +252,25 @@ def test_sweep_drivers_write_reference_shaped_results(tmp_path):
     lp = L.wind_battery_raw(lmp[0], cf, 847.0, 0.0, pem_mw=0.25 * 847.0, h2_price=2.0)
     npv = np.mean([-H.solve(L.wind_battery_raw(l, cf, 847.0, 0.0, pem_mw=0.25 * 847.0, h2_price=2.0))[0] * 1e5 for l in lmp])
     assert rows[0]["NPV"] == pytest.approx(npv, rel=1e-6) and (tmp_path / "wind_PEM.csv").exists()
+
+
+def test_random_designs_and_prices_fuzz(wb):
+    """Seeded fuzz over the whole parameter space of the wind+battery template: sizes over two decades, capacity
+    factors with exact 0 / 1 hours, negative / zero / spiky prices -- stage kernel vs oracle, all optimal."""
+    t, sol = wb
+    rng = np.random.default_rng(7)
+    N = 240
+    pool = SC.pool()
+    base = np.concatenate([pool["day_windows"], pool["cluster_days"]])
+    lmp = base[rng.integers(0, len(base), N)] * rng.lognormal(0, 0.5, (N, 24))
+    lmp[::7] *= -0.3                                   # some negative-price days
+    lmp[::11] = 0.0                                    # all-zero days
+    cf = rng.beta(0.4, 0.8, (N, 24))
+    cf[rng.random((N, 24)) < 0.15] = 0.0
+    cf[rng.random((N, 24)) < 0.05] = 1.0
+    wind = 10 ** rng.uniform(1.5, 3.7, N)              # 30 MW .. 5 GW
+    batt = wind * 10 ** rng.uniform(-2.5, 0.3, N)
+    r = sol.solve_host(lmp, TP.wind_battery_rparams(24, cf, wind, batt))
+    assert (r.status == S.OPTIMAL).all(), np.bincount(r.status)
+    ref = np.array([H.solve(L.wind_battery_raw(lmp[i], cf[i], wind[i], batt[i]))[0] for i in range(N)])
+    assert rel_err(r.obj, ref).max() < REL
