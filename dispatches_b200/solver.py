@@ -21,6 +21,7 @@ import os
 
 _LIB_PATH = Path(os.environ.get("DSP_LP_LIB", Path(__file__).resolve().parent / "csrc" / "libdsp_lp.so"))
 _lib = None
+_PINNED_KEEPALIVE = []
 
 OPTIMAL, MAX_ITER, NUMERICAL = 0, 1, 2
 STATUS_NAMES = {OPTIMAL: "optimal", MAX_ITER: "maxIterations", NUMERICAL: "error"}
@@ -207,7 +208,9 @@ class BatchLPSolver:
         return out
 
     # ------------------------------------------------------------------ host arrays (copies included)
-    def solve_host(self, cparams, rparams=None, want_x=False, want_y=False):
+    def solve_host(self, cparams, rparams=None, want_x=False, want_y=False, out=None):
+        """numpy in / numpy out through dsp_lp_solve_batch_host.  Page-locked arrays (see ``pinned_empty``) skip the
+        library's staging copy; ``out`` = a previous LPResult of the same shape is reused (no allocation)."""
         t = self.t
         cparams = _f64(np.atleast_2d(cparams))
         N = cparams.shape[0]
@@ -216,14 +219,26 @@ class BatchLPSolver:
             rparams = _f64(rparams)
             rstride = 0 if rparams.ndim == 1 else t.Pr
             rptr = rparams.ctypes.data_as(C.c_void_p)
-        obj = np.empty(N); status = np.empty(N, np.int32); iters = np.empty(N, np.int32)
-        x = np.empty((N, t.n)) if want_x else None
-        y = np.empty((N, t.m)) if want_y else None
+        if out is not None:
+            obj, status, iters, x, y = out.obj, out.status, out.iters, out.x, out.y
+        else:
+            obj = np.empty(N); status = np.empty(N, np.int32); iters = np.empty(N, np.int32)
+            x = np.empty((N, t.n)) if want_x else None
+            y = np.empty((N, t.m)) if want_y else None
         vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
         rc = self.lib.dsp_lp_solve_batch_host(self.handle, N, vp(cparams), rptr, rstride, C.byref(self.opts),
                                               vp(obj), vp(status), vp(iters), vp(x), vp(y))
         self._check(rc, "dsp_lp_solve_batch_host")
         return LPResult(obj, status, iters, x, y)
+
+    @staticmethod
+    def pinned_empty(shape, dtype=np.float64):
+        """page-locked numpy array (backed by a pinned torch tensor): host buffers the C ABI can DMA from/to directly"""
+        import torch
+        tt = torch.empty(shape, dtype={np.float64: torch.float64, np.int32: torch.int32}[np.dtype(dtype).type]).pin_memory()
+        a = tt.numpy()
+        _PINNED_KEEPALIVE.append(tt)
+        return a
 
     # ------------------------------------------------------------------
     def to_model_space(self, x):
