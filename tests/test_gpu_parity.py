@@ -274,3 +274,28 @@ def test_random_designs_and_prices_fuzz(wb):
     assert (r.status == S.OPTIMAL).all(), np.bincount(r.status)
     ref = np.array([H.solve(L.wind_battery_raw(lmp[i], cf[i], wind[i], batt[i]))[0] for i in range(N)])
     assert rel_err(r.obj, ref).max() < REL
+
+
+@pytest.mark.parametrize("T", [2, 5, 12, 31, 32])
+def test_stage_kernel_other_horizons(T):
+    """The stage kernel's run-time-T path (only T = 24 is compiled with a fixed horizon): odd / even / full-warp
+    horizons against the band kernel and the oracle."""
+    t = TP.wind_battery(T)
+    stage = S.BatchLPSolver(t, kernel=S.KERNEL_STAGE)
+    band = S.BatchLPSolver(t, kernel=S.KERNEL_BAND)
+    p = SC.pool()
+    rng = np.random.default_rng(T)
+    N = 24
+    h0 = rng.integers(0, 8000, N)
+    idx = h0[:, None] + np.arange(T)[None, :]
+    lmp = p["dalmp_303"][idx] * rng.lognormal(0, 0.3, (N, T))
+    cf = p["dacf_303"][idx]
+    rp = TP.wind_battery_rparams(T, cf, 500.0, 150.0)
+    a = stage.solve_host(lmp, rp, want_x=True)
+    b = band.solve_host(lmp, rp)
+    assert (a.status == S.OPTIMAL).all() and (b.status == S.OPTIMAL).all()
+    assert rel_err(a.obj, b.obj).max() < 1e-7
+    ref = np.array([H.solve(L.wind_battery_raw(lmp[i], cf[i], 500.0, 150.0))[0] for i in range(0, N, 4)])
+    assert rel_err(a.obj[::4], ref).max() < REL
+    bb = np.array([t.instantiate(lmp[i], rp[i])[1] for i in range(N)])
+    assert np.abs(a.x @ t.A.T - bb).max() <= 1e-7 * np.abs(bb).max()

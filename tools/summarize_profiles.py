@@ -68,8 +68,11 @@ def launches(csvfile, dst):
 
 
 if __name__ == "__main__":
-    for name, rep in (("dsp_ipm_band_kernel", G / "prof_r1_band.ncu-rep"), ("dsp_ipm_stage_wb_kernel", G / "prof_r1_stage_v2.ncu-rep")):
+    for name, rep, nlp in (("dsp_ipm_band_kernel<4> (C2, first version)", G / "prof_r1_band.ncu-rep", 10000),
+                           ("dsp_ipm_stage_wb_kernel (C2, first 168-register version)", G / "prof_r1_stage_v2.ncu-rep", 10000),
+                           ("dsp_ipm_stage_wb_kernel (C2, final round-1 version)", G / "prof_r1_stage_final.ncu-rep", 10000),
+                           ("dsp_ipm_band_kernel<1> (C3 nuclear template, 32 LPs, final round-1 version)", G / "prof_r1_band_final.ncu-rep", 32)):
         if rep.exists():
-            summarize(name, rep)
+            summarize(name, rep, nlp)
     if (G / "launches_r1.csv").exists():
         launches(G / "launches_r1.csv", OUT / "launches_r1.csv")
