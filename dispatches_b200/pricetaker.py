@@ -27,7 +27,8 @@ _SOLVERS = {}
 def get_solver(kind, T, **kw) -> BatchLPSolver:
     key = (kind, T, tuple(sorted(kw.items())))
     if key not in _SOLVERS:
-        builder = dict(wind_battery=TP.wind_battery, wind_battery_pem=TP.wind_battery_pem, nuclear=TP.nuclear,
+        builder = dict(wind_battery=TP.wind_battery, wind_battery_design=TP.wind_battery_design,
+                       wind_battery_pem=TP.wind_battery_pem, nuclear=TP.nuclear,
                        fossil_surrogate=TP.fossil_surrogate)[kind]
         _SOLVERS[key] = BatchLPSolver(builder(T, **kw))
     return _SOLVERS[key]
@@ -111,12 +112,15 @@ def _lmps(input_params, T):
 
 
 def wind_battery_optimize(n_time_points, input_params, verbose=False, want_solution=True):
-    if input_params.get("design_opt", False):
-        raise NotImplementedError("design_opt=True is not on the batched GPU path (fixed-design sweeps only)")
     T = int(n_time_points)
+    design = bool(input_params.get("design_opt", False))
+    if design and not input_params.get("extant_wind", True):
+        raise NotImplementedError("design_opt with a free wind size is not on the batched GPU path")
     lmp = _lmps(input_params, T)
     cf = _capacity_factors(input_params, T)
-    sol = get_solver("wind_battery", T, extant_wind=bool(input_params.get("extant_wind", True)))
+    sol = get_solver("wind_battery_design" if design else "wind_battery", T,
+                     extant_wind=bool(input_params.get("extant_wind", True)))
+    want_solution = want_solution or design          # the optimal battery size is read from the solution
     rp = TP.wind_battery_rparams(T, cf, input_params["wind_mw"], input_params["batt_mw"])
     if rp.shape[0] == 1:
         rp = rp[0]
@@ -129,8 +133,10 @@ def wind_battery_optimize(n_time_points, input_params, verbose=False, want_solut
     N = lmp.shape[0]
     sizes = dict(wind_kw=np.broadcast_to(np.asarray(input_params["wind_mw"], float) * 1e3, (N,)),
                  batt_kw=np.broadcast_to(np.asarray(input_params["batt_mw"], float) * 1e3, (N,)))
-    return PriceTakerResult("wind_battery", T, lmp, r.obj, r.status, r.iters,
-                            sol.to_model_space(r.x) if want_solution else None, sol.t.col_names, sizes)
+    xm = sol.to_model_space(r.x) if want_solution else None
+    if design:                                        # optimised size: value(m.battery_system_capacity)
+        sizes["batt_kw"] = xm[:, sol.t.col_names.index("blk[0].fs.battery.nameplate_power")].copy()
+    return PriceTakerResult("wind_battery", T, lmp, r.obj, r.status, r.iters, xm, sol.t.col_names, sizes)
 
 
 def wind_battery_pem_optimize(time_points, input_params, verbose=False, want_solution=True):

@@ -86,6 +86,54 @@ def wind_battery(T: int, extant_wind: bool = True) -> LPTemplate:
     return t
 
 
+def wind_battery_design(T: int, extant_wind: bool = True) -> LPTemplate:
+    """wind_battery_optimize with design_opt=True, extant_wind=True (the reference's default_input_params,
+    load_parameters.py:123-140; wind_battery_LMP.py:212-216): the battery nameplate power is a decision.
+
+    Formulated the way the reference's MultiPeriodModel does it: one nameplate_power column PER PERIOD with the
+    link equalities P[t] = P[t+1] (wind_battery_LMP.py:35), so the constraint matrix stays block banded in time (a
+    single global capacity column would be dense; a rank-one (Woodbury) update of the band factor for it was tried and
+    is numerically unstable -- DESIGN.md 6b).  battery_system_capacity >= nameplate_power (:219) is tight (positive
+    cost), so its capital and O&M cost sit on P[0].  nameplate_energy = 4 P (RE_flowsheet.py:155-156) is substituted.
+    rparams = [wind_kw*cf_t (T), unused, wind_kw] (same layout as wind_battery)."""
+    if not extant_wind:
+        raise NotImplementedError("design_opt with a free wind size puts cf_t into the constraint matrix (not batched)")
+    iW = T + 1
+    B = TemplateBuilder(f"wind_battery_design_T{T}", Pc=T, Pr=T + 2)
+    ann = 52.0 / (T / 168.0)
+    k_rev = -1e-5 * PA * ann * 1e-3
+    cap = BATT_CAP_COST_KW + BATT_CAP_COST_KWH * DURATION
+    g, i, o, s, e, Pn = {}, {}, {}, {}, {}, {}
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        g[t] = B.var(p + "splitter.grid_elec[0]")
+        i[t] = B.var(p + "battery.elec_in[0]")
+        o[t] = B.var(p + "battery.elec_out[0]")
+        s[t] = B.var(p + "battery.state_of_charge[0]", fix=(0.0 if t == T - 1 else None))
+        e[t] = B.var(p + "battery.energy_throughput[0]")
+        Pn[t] = B.var(p + "battery.nameplate_power")
+        B.cost(g[t], (0.0, {t: k_rev})); B.cost(o[t], (0.0, {t: k_rev}))
+    B.cost(Pn[0], 1e-5 * (cap + PA * ann * T * BATT_OP_COST / 8760.0))
+    for t in range(T):
+        row = {s[t]: 1.0, i[t]: -ETA_C, o[t]: 1.0 / ETA_D}
+        if t > 0:
+            row[s[t - 1]] = -1.0
+        B.eq(f"soc[{t}]", row)
+        row = {e[t]: 1.0, i[t]: -0.5, o[t]: -0.5}
+        if t > 0:
+            row[e[t - 1]] = -1.0
+        B.eq(f"throughput[{t}]", row)
+        B.le(f"power_bound_in[{t}]", {i[t]: 1.0, Pn[t]: -1.0})
+        B.le(f"power_bound_out[{t}]", {o[t]: 1.0, Pn[t]: -1.0})
+        B.le(f"soc_bound[{t}]", {s[t]: 1.0, e[t]: DEGRADATION, Pn[t]: -DURATION})
+        B.le(f"wind[{t}]", {g[t]: 1.0, i[t]: 1.0}, (0.0, {t: 1.0}))
+        if t < T - 1:
+            B.eq(f"link_nameplate[{t}]", {Pn[t]: 1.0, Pn[t + 1]: -1.0})
+    B.obj_const((0.0, {iW: 1e-5 * (PA * ann * T * WIND_OP_COST / 8760.0)}))
+    B.meta.update(kind="wind_battery_design", T=T, ann=ann)
+    return B.build()
+
+
 def wind_battery_rparams(T, cf, wind_mw, batt_mw, pem_mw=None):
     """rparams rows for wind_battery / wind_battery_pem: cf [N,T] or [T]; sizes scalar or [N]."""
     cf = np.atleast_2d(np.asarray(cf, float))

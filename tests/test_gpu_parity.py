@@ -234,7 +234,7 @@ def test_reference_shaped_api():
     soc, wind_gen, b2g, w2g, w2b, rev, lmps, wcap, bcap, ann, npv = PT.record_results(res, 0)
     assert len(soc) == 24 and soc[-1] == 0.0 and wcap == pytest.approx(W) and npv == pytest.approx(res.NPV[0])
     with pytest.raises(NotImplementedError):
-        PT.wind_battery_optimize(24, dict(params, design_opt=True))
+        PT.wind_battery_optimize(24, dict(params, design_opt=True, extant_wind=False))
 
 
 def test_sweep_drivers_write_reference_shaped_results(tmp_path):
@@ -299,3 +299,27 @@ def test_stage_kernel_other_horizons(T):
     assert rel_err(a.obj[::4], ref).max() < REL
     bb = np.array([t.instantiate(lmp[i], rp[i])[1] for i in range(N)])
     assert np.abs(a.x @ t.A.T - bb).max() <= 1e-7 * np.abs(bb).max()
+
+
+def test_design_opt_border_column():
+    """design_opt=True (battery size is a decision; per-period nameplate columns + link rows, half bandwidth > 8 so the
+    <16> instantiation of the band kernel): objective and optimal size against the oracle, through the reference API."""
+    lmp, cf, W, P = SC.c2(48)
+    lmp[::3] *= 40.0                                 # scarcity days make a battery worth building
+    t = TP.wind_battery_design(24)
+    sol = S.BatchLPSolver(t)
+    rp = TP.wind_battery_rparams(24, cf, W, 0.0)[0]
+    r = sol.solve_host(lmp, rp, want_x=True)
+    assert (r.status == S.OPTIMAL).all(), np.bincount(r.status)
+    sols = [H.solve(L.wind_battery_raw(l, cf, W, 0.0, design_opt=True, extant_wind=True)) for l in lmp]
+    ref = np.array([s[0] for s in sols])
+    assert rel_err(r.obj, ref).max() < REL
+    params = {"wind_mw": W, "wind_mw_ub": 10000, "batt_mw": 0.0, "design_opt": True, "extant_wind": True,
+              "wind_resource": cf, "DA_LMPs": lmp}
+    res = PT.wind_battery_optimize(24, params)
+    lp0 = L.wind_battery_raw(lmp[0], cf, W, 0.0, design_opt=True, extant_wind=True)
+    p_ref = np.array([s[1][lp0.meta["Bc"]] for s in sols])
+    assert p_ref.max() > 1e3                                     # some scenario builds > 1 MW
+    big = p_ref > 1e3
+    assert np.allclose(res.sizes["batt_kw"][big], p_ref[big], rtol=2e-4)
+    assert np.all(res.sizes["batt_kw"][~big] < 1e3 * 1.01 + 50.0)

@@ -18,7 +18,7 @@ def reference_params(lmp, cf, W, P, **kw):
 def test_design_opt_is_refused_not_silently_fixed():
     lmp, cf, W, P = SC.c2(2)
     with pytest.raises(NotImplementedError):
-        PT.wind_battery_optimize(24, reference_params(lmp, cf, W, P, design_opt=True))
+        PT.wind_battery_optimize(24, reference_params(lmp, cf, W, P, design_opt=True, extant_wind=False))
     with pytest.raises(NotImplementedError):
         PT.wind_battery_pem_optimize(24, reference_params(lmp, cf, W, P, design_opt="PEM", pem_mw=100, h2_price_per_kg=2))
 

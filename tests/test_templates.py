@@ -101,3 +101,20 @@ def test_scenarios_are_seeded_and_keep_hard_cases():
     assert (a == 0).mean() > 0.05 and a.max() > 5000.0      # exact zeros and scarcity spikes survive
     lmp, cf, w, p = SC.c5(2, 2, 48)
     assert lmp.shape == (2 * 2 * 48, 24) and cf.shape == lmp.shape and w.shape == (192,)
+
+
+def test_wind_battery_design_opt_template_matches_raw_oracle():
+    """design_opt=True, extant_wind=True: per-period nameplate_power columns + link rows keep the matrix banded."""
+    t = TP.wind_battery_design(24)
+    assert t.w <= 16
+    lmp, cf, W, P = SC.c2(6)
+    lmp[0] *= 40.0                                   # a scarcity day: the optimal battery is not zero
+    rp = TP.wind_battery_rparams(24, cf, W, 0.0)[0]
+    jP = t.col_names.index("blk[0].fs.battery.nameplate_power")
+    sizes = []
+    for k in range(6):
+        a, x = solve_template(t, lmp[k], rp)
+        b, xr = H.solve(L.wind_battery_raw(lmp[k], cf, W, 0.0, design_opt=True, extant_wind=True))
+        assert a == pytest.approx(b, rel=1e-10, abs=1e-8)
+        sizes.append(x[jP])
+    assert max(sizes) > 1.0                          # kW
