@@ -33,10 +33,7 @@ def solve_sharded(solve_fn, N, group=None):
         gathered = torch.empty(per * world, dtype=v.dtype, device=v.device)
         dist.all_gather_into_tensor(gathered, pad, group=group) if v.is_cuda else \
             dist.all_gather(list(gathered.view(world, per).unbind(0)), pad, group=group)
-        full = torch.empty(N, dtype=v.dtype, device=v.device)
-        g2 = gathered.view(world, per)
-        for r in range(world):
-            ir = shard_indices(N, r, world)
-            full[torch.as_tensor(ir, device=v.device)] = g2[r, : len(ir)]
+        # shard r holds the indices r, r+world, r+2*world, ...: transposing [world, per] interleaves them back
+        full = gathered.view(world, per).transpose(0, 1).reshape(-1)[:N].contiguous()
         out[k] = full
     return out

@@ -51,3 +51,21 @@ def test_no_cpu_fallback_in_product():
         pytest.skip("checks the no-GPU failure mode")
     with pytest.raises(RuntimeError):
         solver.BatchLPSolver(TP.nuclear(4)).solve_host(np.zeros((1, 4)))
+
+
+def test_argument_errors_are_reported_without_a_gpu(cuda_solver_lib):
+    """Bad descriptors / null handles come back as DSP_E_ARG with a message (no CUDA call is made before the checks)."""
+    import ctypes as C
+    from dispatches_b200 import solver
+    lib = cuda_solver_lib
+    d = solver._Desc(m=0, n=5, nb=0, w=0, Pc=1, Pr=0)
+    h = C.c_void_p()
+    assert lib.dsp_lp_template_create(C.byref(d), C.byref(h)) == -1
+    assert b"bad dimensions" in lib.dsp_lp_last_error()
+    assert lib.dsp_lp_solve_batch(None, 4, None, None, 0, None, None, None, None, None, None, None) == -1
+    assert lib.dsp_lp_solve_batch_host(None, 4, None, None, 0, None, None, None, None, None, None) == -1
+    o = solver._Opts()
+    lib.dsp_lp_default_opts(C.byref(o))
+    assert (o.tol, o.feas_tol, o.max_iter, o.kernel) == (1e-9, 1e-9, 60, solver.KERNEL_AUTO) and o.reg_primal == 1e-8
+    sd = solver._StageWB(T=40)
+    assert lib.dsp_lp_template_set_stage_wb(None, C.byref(sd)) == -1
