@@ -535,6 +535,18 @@ __global__ void __launch_bounds__(32 * DSP_STAGE_WPB, DSP_STAGE_MINB) dsp_ipm_st
     }
 }
 
+// FP64 FMA micro-benchmark: the measured denominator of the FP64 roofline fraction bench.py reports (the driver's
+// MEASURED_PEAKS.json has HBM and bf16 peaks only).  8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) dsp_fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (r == 123.456) out[0] = r;      // never true: keeps the chains alive
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -587,6 +599,32 @@ struct dsp_template {
 extern "C" {
 
 const char *dsp_lp_version(void) { return DSP_VERSION; }
+
+double dsp_lp_fp64_peak_tflops(void) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1.0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double *d = nullptr;
+    if (cudaMalloc((void **)&d, 8) != cudaSuccess) return -1.0;
+    const int iters = 8192, blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    dsp_fp64_peak_kernel<<<blocks, threads>>>(d, 64, 0.999999, 1e-9);       // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        dsp_fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = ms < best ? ms : best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    return flops / (best * 1e-3) / 1e12;
+}
 #ifdef DSP_PHASES
 int dsp_lp_phases(unsigned long long *out16, int reset) {
     cudaMemcpyFromSymbol(out16, g_phase, sizeof(unsigned long long) * 16);

@@ -30,7 +30,7 @@ KERNEL_AUTO, KERNEL_BAND, KERNEL_STAGE = 0, 1, 2
 
 EXPORTS = ["dsp_lp_template_create", "dsp_lp_template_destroy", "dsp_lp_template_set_stage_wb", "dsp_lp_default_opts", "dsp_lp_solve_batch",
            "dsp_lp_solve_batch_host", "dsp_lp_launch_count", "dsp_lp_last_launch", "dsp_lp_last_error",
-           "dsp_lp_version"]
+           "dsp_lp_version", "dsp_lp_fp64_peak_tflops"]
 
 
 class _ParamMap(C.Structure):
@@ -87,8 +87,14 @@ def load_library():
     lib.dsp_lp_last_launch.restype = C.c_int
     lib.dsp_lp_last_error.restype = C.c_char_p
     lib.dsp_lp_version.restype = C.c_char_p
+    lib.dsp_lp_fp64_peak_tflops.restype = C.c_double
     _lib = lib
     return lib
+
+
+def fp64_peak_tflops() -> float:
+    """measured FP64 FMA peak of the current device (TFLOP/s)"""
+    return float(load_library().dsp_lp_fp64_peak_tflops())
 
 
 def launch_count() -> int:

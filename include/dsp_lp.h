@@ -120,6 +120,9 @@ int64_t dsp_lp_launch_count(void);
 int dsp_lp_last_launch(int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *problems_per_cta);
 const char *dsp_lp_last_error(void);
 const char *dsp_lp_version(void);
+/* measured FP64 FMA throughput of the current device in TFLOP/s (micro-benchmark; -1 on error): denominator of the
+ * FP64 roofline fraction reported by bench.py */
+double dsp_lp_fp64_peak_tflops(void);
 
 #ifdef __cplusplus
 }
