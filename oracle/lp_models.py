@@ -377,3 +377,50 @@ def fossil_surrogate_raw(lmp, par=None):
     B.lb[v["hp", 0]] = B.ub[v["hp", 0]] = P["hot_init"]
     B.lb[v["Pp", 0]] = B.ub[v["Pp", 0]] = P["pprev0"]
     return B.finish(dict(kind="fossil_surrogate", T=T, v=v))
+
+
+# --------------------------------------------------------------------------------------
+# A.3 (report variant)  nuclear + PEM (+tank, +turbine) price-taker, price_taker_analysis.py:116-322
+# --------------------------------------------------------------------------------------
+def nuclear_report_raw(lmp, h2_price, pem_cap_mw, pem_capex=400.0, tank_cap=0.0, turbine_cap=0.0, demand=400.0 * 20,
+                       vom_pem=0.0, plant_life=30, tax_rate=0.2, discount_rate=0.08):
+    """Raw LP of run_exhaustive_enumeration's inner solve (price_taker_analysis.py:353-403) for T = len(lmp) hours:
+    build_ne_flowsheet rows (:143-170), capacity rows (:199-213), demand bound (:219-220), cash flow (:239-254),
+    NPV pieces (:274-308), annualised objective (:318-322, maximise -> minimise the negative)."""
+    lmp = np.asarray(lmp, float); T = lmp.size
+    B = _Builder(); v = {}
+    fom_pem = 0.03 * pem_capex
+    capex = pem_capex * 1000.0 * pem_cap_mw + 29.0 * 33.3 * tank_cap + 947.0 * 1000.0 * turbine_cap
+    fom = 1000.0 * fom_pem * pem_cap_mw + 1000.0 * 7.0 * turbine_cap + 120.0 * 1000.0 * 400.0
+    dep = capex / plant_life
+    cf = (1.0 - (1.0 + discount_rate) ** (-plant_life)) / discount_rate
+    # objective: net_profit - capex/cf = dep + (1-tax)(sum cash - fom - dep) - capex/cf
+    k = 1.0 - tax_rate
+    for t in range(T):
+        p = f"period[{t + 1}].fs."
+        v["np", t] = B.var(p + "np_power", fix=400.0)
+        v["g", t] = B.var(p + "np_to_grid")
+        v["e", t] = B.var(p + "np_to_electrolyzer")
+        v["h", t] = B.var(p + "h2_production")
+        v["H", t] = B.var(p + "tank_holdup")
+        v["Hp", t] = B.var(p + "tank_holdup_previous")
+        v["u", t] = B.var(p + "h2_to_pipeline", ub=demand)
+        v["tb", t] = B.var(p + "h2_to_turbine")
+        v["tp", t] = B.var(p + "h2_turbine_power")
+        v["n", t] = B.var(p + "net_power")
+        B.eq({v["np", t]: 1.0, v["g", t]: -1.0, v["e", t]: -1.0})
+        B.eq({v["h", t]: 1.0, v["e", t]: -20.0})
+        B.eq({v["H", t]: 1.0, v["Hp", t]: -1.0, v["h", t]: -1.0, v["u", t]: 1.0, v["tb", t]: 1.0})
+        B.eq({v["tp", t]: 1.0, v["tb", t]: -0.0125})
+        B.eq({v["n", t]: 1.0, v["g", t]: -1.0, v["tp", t]: -1.0})
+        B.le({v["e", t]: 1.0}, pem_cap_mw)
+        B.le({v["H", t]: 1.0}, tank_cap)
+        B.le({v["tp", t]: 1.0}, turbine_cap)
+        B.cost(v["u", t], -k * h2_price)
+        B.cost_lmp(v["n", t], t, -k, lmp)
+        B.cost(v["e", t], k * vom_pem); B.cost(v["tp", t], k * 4.25); B.cost(v["np", t], k * 2.3)
+    for t in range(T - 1):
+        B.eq({v["H", t]: 1.0, v["Hp", t + 1]: -1.0})
+    B.lb[v["Hp", 0]] = B.ub[v["Hp", 0]] = 0.0
+    B.c0 = -(dep + k * (-fom - dep) - capex / cf)
+    return B.finish(dict(kind="nuclear_report", T=T, v=v, capex=capex, fom=fom))

@@ -49,6 +49,9 @@ def main():
         p = pd.read_parquet(rc / "data" / f"303_LMPs_15_reserve_{shortfall}_shortfall.parquet")
         for col, key in (("LMP", "rt_lmp"), ("LMP DA", "da_lmp"), ("303_WIND_1-RTCF", "rt_cf"), ("303_WIND_1-DACF", "da_cf")):
             extra[f"pq{shortfall}_{key}"] = p[col].values
+    nr = pd.read_csv(REF / "case_studies" / "nuclear_case" / "report" / "rts_gmlc_15_500.csv")
+    extra["nuc_report_lmp_rt"] = nr["LMP"].values          # get_lmp_data, price_taker_analysis.py:45-113
+    extra["nuc_report_lmp_da"] = nr["LMP DA"].values
     np.savez_compressed(OUT.parent.parent / "dispatches_b200" / "data" / "lmp_pool.npz", day_windows=day_windows, cluster_days=cluster_days,
                         dalmp_303=df["303_DALMP"].values, dacf_303=df["303_WIND_1-DACF"].values, **extra)
 

@@ -118,3 +118,16 @@ def test_wind_battery_design_opt_template_matches_raw_oracle():
         assert a == pytest.approx(b, rel=1e-10, abs=1e-8)
         sizes.append(x[jP])
     assert max(sizes) > 1.0                          # kW
+
+
+def test_nuclear_report_enumeration_presolve_equals_the_full_lp():
+    """run_exhaustive_enumeration (price_taker_analysis.py:353-425): the per-hour closed form of the product equals the
+    full multi-period LP (tank and turbine capacity 0) solved by the oracle, on two weeks of the report's RT prices."""
+    from dispatches_b200 import run_pricetaker as RP
+    lmp = SC.pool()["nuc_report_lmp_rt"][2000:2336]
+    res = RP.run_exhaustive_enumeration(lmp, pem_capex=400.0, h2_prices=(0.75, 1.5), pem_fractions=(0.05, 0.5))
+    for i1, hp in enumerate((0.75, 1.5)):
+        for i2, pc in enumerate((0.05, 0.5)):
+            obj, x = H.solve(L.nuclear_report_raw(lmp, hp, pc * 400.0, pem_capex=400.0))
+            assert res["net_npv"][f"{i1}{i2}"] == pytest.approx(-obj / 1e6, rel=1e-9)
+    assert 0.0 <= res["pem_cap_factor"]["11"] <= 1.0 and res["solver_stat"]["00"] == "optimal"
