@@ -140,15 +140,19 @@ def wind_battery_optimize(n_time_points, input_params, verbose=False, want_solut
 
 
 def wind_battery_pem_optimize(time_points, input_params, verbose=False, want_solution=True):
-    if input_params.get("design_opt", False):
-        raise NotImplementedError("design_opt != False is not on the batched GPU path (fixed-design sweeps only)")
+    mode = input_params.get("design_opt", False)
+    if mode not in (False, "PEM") or (mode == "PEM" and not input_params.get("extant_wind", True)):
+        raise NotImplementedError("only design_opt False and \"PEM\" (extant wind) are on the batched GPU path")
+    pem_design = mode == "PEM"
     T = int(time_points)
     lmp = _lmps(input_params, T)
     N = lmp.shape[0]
     cf = _capacity_factors(input_params, T)
-    batt = np.asarray(input_params["batt_mw"], float)
+    batt = np.zeros(1) if pem_design else np.asarray(input_params["batt_mw"], float)   # "PEM" fixes the battery at 0 (:228)
     with_batt = bool(np.any(batt > 0))
-    sol = get_solver("wind_battery_pem", T, with_battery=with_batt, extant_wind=bool(input_params.get("extant_wind", True)))
+    want_solution = want_solution or pem_design
+    sol = get_solver("wind_battery_pem", T, with_battery=with_batt, extant_wind=bool(input_params.get("extant_wind", True)),
+                     pem_design=pem_design)
     rp = TP.wind_battery_rparams(T, cf, input_params["wind_mw"], batt, pem_mw=input_params["pem_mw"])
     rp = rp[0] if rp.shape[0] == 1 else rp
     h2 = np.broadcast_to(np.asarray(input_params["h2_price_per_kg"], float), (N,))
@@ -157,8 +161,10 @@ def wind_battery_pem_optimize(time_points, input_params, verbose=False, want_sol
     sizes = dict(wind_kw=np.broadcast_to(np.asarray(input_params["wind_mw"], float) * 1e3, (N,)),
                  batt_kw=np.broadcast_to(batt * 1e3, (N,)),
                  pem_kw=np.broadcast_to(np.asarray(input_params["pem_mw"], float) * 1e3, (N,)), h2_price=h2)
-    return PriceTakerResult("wind_battery_pem", T, lmp, r.obj, r.status, r.iters,
-                            sol.to_model_space(r.x) if want_solution else None, sol.t.col_names, sizes)
+    xm = sol.to_model_space(r.x) if want_solution else None
+    if pem_design:                                    # optimised size: value(m.pem_system_capacity)
+        sizes["pem_kw"] = xm[:, sol.t.col_names.index("pem_system_capacity[0]")].copy()
+    return PriceTakerResult("wind_battery_pem", T, lmp, r.obj, r.status, r.iters, xm, sol.t.col_names, sizes)
 
 
 def nuclear_dispatch_optimize(n_time_points, lmps, want_solution=False, **flowsheet_options):

@@ -146,24 +146,29 @@ def wind_battery_rparams(T, cf, wind_mw, batt_mw, pem_mw=None):
     return np.ascontiguousarray(np.concatenate(cols, axis=1))
 
 
-def wind_battery_pem(T: int, with_battery: bool = True, extant_wind: bool = True) -> LPTemplate:
+def wind_battery_pem(T: int, with_battery: bool = True, extant_wind: bool = True, pem_design: bool = False) -> LPTemplate:
     """wind_battery_pem_optimize with design_opt=False (wind_battery_PEM_LMP.py:180-298).
 
     Differences from wind_battery: PEM electricity column with H2 revenue (:276), only the initial energy
     throughput is fixed (:217) so the state of charge is periodic (s0[0] = s[T-1], a cyclic link), and
     run_pricetaker_wind_PEM.py:37-41 sweeps with batt_mw = 0 (``with_battery=False`` drops the battery
-    columns instead of bounding them by 0)."""
+    columns instead of bounding them by 0).  ``pem_design=True`` is the reference's design_opt="PEM" mode
+    (pem_ratio None in run_pricetaker_wind_PEM.py:36-37): pem_system_capacity is a decision -- one capacity column per
+    period with link equalities (keeps the matrix banded, see wind_battery_design), its cost on the first copy."""
     iP, iW, iPem = T, T + 1, T + 2
     ih2 = T
-    B = TemplateBuilder(f"wind_battery_pem_T{T}" + ("" if with_battery else "_nobatt"), Pc=T + 1, Pr=T + 3)
+    B = TemplateBuilder(f"wind_battery_pem_T{T}" + ("" if with_battery else "_nobatt") + ("_pemdesign" if pem_design else ""),
+                        Pc=T + 1, Pr=T + 3)
     ann = 52.0 / (T / 168.0)
     k_rev = -1e-5 * PA * ann * 1e-3
     k_h2 = -1e-5 * PA * ann * PEM_ELEC_TO_MOL / H2_MOLS_PER_KG * 3600.0
-    g, i, o, s, e, pe = {}, {}, {}, {}, {}, {}
+    g, i, o, s, e, pe, pc = {}, {}, {}, {}, {}, {}, {}
     for t in range(T):
         p = f"blk[{t}].fs."
         g[t] = B.var(p + "splitter.grid_elec[0]")
-        pe[t] = B.var(p + "pem.electricity[0]", ub=(0.0, {iPem: 1.0}))         # :239
+        pe[t] = B.var(p + "pem.electricity[0]", ub=(None if pem_design else (0.0, {iPem: 1.0})))         # :239
+        if pem_design:
+            pc[t] = B.var(f"pem_system_capacity[{t}]")
         B.cost(g[t], (0.0, {t: k_rev}))
         B.cost(pe[t], (1e-5 * PA * ann * PEM_VAR_COST, {ih2: k_h2}))            # :276, pem var cost :268
         if with_battery:
@@ -185,9 +190,15 @@ def wind_battery_pem(T: int, with_battery: bool = True, extant_wind: bool = True
             B.eq(f"throughput[{t}]", row)
             B.le(f"soc_bound[{t}]", {s[t]: 1.0, e[t]: DEGRADATION}, (0.0, {iP: DURATION}))
         B.le(f"wind[{t}]", wind_row, (0.0, {t: 1.0}))
+        if pem_design:
+            B.le(f"pem_max_p[{t}]", {pe[t]: 1.0, pc[t]: -1.0})               # :239
+            if t < T - 1:
+                B.eq(f"link_pem_capacity[{t}]", {pc[t]: 1.0, pc[t + 1]: -1.0})
     cap = BATT_CAP_COST_KW + BATT_CAP_COST_KWH * DURATION
+    if pem_design:
+        B.cost(pc[0], 1e-5 * (PEM_CAP_COST + PA * ann * T * PEM_OP_COST / 8760.0))
     om = {iW: 1e-5 * ((0.0 if extant_wind else WIND_CAP_COST) + PA * ann * T * WIND_OP_COST / 8760.0),
-          iPem: 1e-5 * (PEM_CAP_COST + PA * ann * T * PEM_OP_COST / 8760.0)}
+          iPem: 0.0 if pem_design else 1e-5 * (PEM_CAP_COST + PA * ann * T * PEM_OP_COST / 8760.0)}
     om[iP] = 1e-5 * (cap + PA * ann * T * BATT_OP_COST / 8760.0)
     B.obj_const((0.0, om))
     B.meta.update(kind="wind_battery_pem", T=T, ann=ann, with_battery=with_battery)

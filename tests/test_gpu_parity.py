@@ -323,3 +323,18 @@ def test_design_opt_border_column():
     big = p_ref > 1e3
     assert np.allclose(res.sizes["batt_kw"][big], p_ref[big], rtol=2e-4)
     assert np.all(res.sizes["batt_kw"][~big] < 1e3 * 1.01 + 50.0)
+
+
+def test_design_opt_pem_mode():
+    """design_opt="PEM" (run_pricetaker_wind_PEM.py:36-37, pem_ratio None): PEM size optimised, battery fixed at 0."""
+    lmp, cf, W, P = SC.c2(40)
+    params = {"wind_mw": W, "wind_mw_ub": 10000, "batt_mw": 0.0, "pem_mw": 355.0, "h2_price_per_kg": 2.5,
+              "design_opt": "PEM", "extant_wind": True, "wind_resource": cf, "DA_LMPs": lmp}
+    res = PT.wind_battery_pem_optimize(24, params)
+    assert (res.status == S.OPTIMAL).all()
+    sols = [H.solve(L.wind_battery_raw(l, cf, W, 0.0, pem_mw=355.0, h2_price=2.5, design_opt="PEM")) for l in lmp]
+    ref = np.array([s[0] for s in sols])
+    assert rel_err(res.obj, ref).max() < REL
+    lp0 = L.wind_battery_raw(lmp[0], cf, W, 0.0, pem_mw=355.0, h2_price=2.5, design_opt="PEM")
+    pem_ref = np.array([s[1][lp0.meta["Pc"]] for s in sols])
+    assert np.allclose(res.sizes["pem_kw"], pem_ref, rtol=1e-4, atol=5.0)

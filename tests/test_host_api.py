@@ -20,7 +20,7 @@ def test_design_opt_is_refused_not_silently_fixed():
     with pytest.raises(NotImplementedError):
         PT.wind_battery_optimize(24, reference_params(lmp, cf, W, P, design_opt=True, extant_wind=False))
     with pytest.raises(NotImplementedError):
-        PT.wind_battery_pem_optimize(24, reference_params(lmp, cf, W, P, design_opt="PEM", pem_mw=100, h2_price_per_kg=2))
+        PT.wind_battery_pem_optimize(24, reference_params(lmp, cf, W, P, design_opt=True, pem_mw=100, h2_price_per_kg=2))
 
 
 def test_capacity_factor_dict_and_lmp_shapes():
