@@ -62,7 +62,8 @@ struct KParams {
     double *obj, *x_out, *y_out;
     int *status, *iters;
     unsigned long long *ticket;
-    int prob_doubles;             // per-warp shared-memory doubles
+    double *ws;                   // non-null: per-warp work regions live in this global-memory workspace (long horizons)
+    int prob_doubles;             // per-warp work-region doubles
     int prob_off;                 // byte offset of the first per-warp region
 };
 
@@ -339,7 +340,7 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
             double acc = W.c[j] - zj;
             for (int q = H.At_ptr[j]; q < H.At_ptr[j + 1]; ++q) acc -= H.At_val[q] * W.y[H.At_idx[q]];
             const double rxj = frcpd(xj);
-            double t = zj * rxj + reg;
+            double t = zj * rxj + (xj > 1.0 ? reg * rxj * rxj : reg);      // proximal term, scale invariant for x > 1
             if (j < nb) {
                 const double sj = W.s[j], wj = W.wv[j], uj = W.u[j];
                 acc += wj;
@@ -472,7 +473,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) dsp_ipm_band_kernel(const K
         hot = smem + 16;
     }
     const Hot H = hot_views(hot, P);
-    double *base = (double *)(smem + P.prob_off) + (size_t)warp * P.prob_doubles;
+    double *base = P.ws ? P.ws + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)P.prob_doubles
+                        : (double *)(smem + P.prob_off) + (size_t)warp * P.prob_doubles;
     Work W;
     const int n = P.n, nb = P.nb, m = P.m;
     W.x = base; W.z = W.x + n; W.c = W.z + n; W.rd = W.c + n; W.d = W.rd + n; W.dx = W.d + n; W.cor = W.dx + n; W.rx = W.cor + n;
@@ -578,6 +580,8 @@ int upload(const std::vector<T> &h, T **d) {
 struct dsp_template {
     KParams kp;
     bool has_stage;
+    mutable double *ws;            // global workspace for templates whose work region exceeds shared memory
+    mutable size_t ws_bytes;
     stagewb::StageParams sp;
     int stage_blocks_per_sm;
     int device;
@@ -710,7 +714,7 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     dsp_template *T = new dsp_template();
     memset(&T->kp, 0, sizeof(KParams));
     T->cap_N = 0; T->cap_x = T->cap_y = false; T->cap_rp_rows = 0;
-    T->has_stage = false; T->stage_blocks_per_sm = 0;
+    T->has_stage = false; T->stage_blocks_per_sm = 0; T->ws = nullptr; T->ws_bytes = 0;
     T->h_cp = T->h_rp = T->h_obj = T->h_x = T->h_y = nullptr; T->h_status = T->h_iters = nullptr;
     T->d_cp = T->d_rp = T->d_obj = T->d_x = T->d_y = nullptr; T->d_status = T->d_iters = nullptr;
     T->stream = nullptr; T->stream2 = nullptr;
@@ -805,6 +809,7 @@ int dsp_lp_template_set_stage_wb(dsp_template *T, const dsp_stage_wb_desc *d) {
 void dsp_lp_template_destroy(dsp_template *T) {
     if (!T) return;
     for (void *p : T->dev_allocs) cudaFree(p);
+    cudaFree(T->ws);
     cudaFree(T->d_cp); cudaFree(T->d_rp); cudaFree(T->d_obj); cudaFree(T->d_x); cudaFree(T->d_y);
     cudaFree(T->d_status); cudaFree(T->d_iters);
     cudaFreeHost(T->h_cp); cudaFreeHost(T->h_rp); cudaFreeHost(T->h_obj); cudaFreeHost(T->h_x); cudaFreeHost(T->h_y);
@@ -860,9 +865,12 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         off = 16;
         warps = (long long)((budget - off) / prob_bytes);
     }
+    bool ws_mode = false;
     if (warps < 1) {
-        g_err = "dsp_lp_solve_batch: one LP does not fit in shared memory (" + std::to_string(prob_bytes) + " bytes)";
-        return DSP_E_SMEM;
+        // long horizons: the per-LP work region does not fit in shared memory -> same kernel, work regions in a global
+        // workspace (L2-resident sweeps; slower per LP, but a full-year T = 8736 LP runs at all)
+        ws_mode = true;
+        warps = 2;
     }
     warps = std::min<long long>(warps, kMaxWarps);
     long long ctas = std::min<long long>(T->sm_count, (N + warps - 1) / warps);
@@ -873,7 +881,20 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
     }
     K.hot_in_smem = hot_in_smem;
     K.prob_off = (int)off;
-    const size_t smem = off + (size_t)warps * prob_bytes;
+    K.ws = nullptr;
+    size_t smem = off + (size_t)warps * prob_bytes;
+    if (ws_mode) {
+        const size_t need = (size_t)ctas * (size_t)warps * prob_bytes;
+        if (need > T->ws_bytes) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(T->ws);
+            T->ws = nullptr; T->ws_bytes = 0;
+            CK(cudaMalloc((void **)&T->ws, need));
+            T->ws_bytes = need;
+        }
+        K.ws = T->ws;
+        smem = 16;
+    }
     CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
     switch (K.w) {
         case 1: dsp_ipm_band_kernel<1><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K); break;

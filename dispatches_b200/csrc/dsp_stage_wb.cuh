@@ -242,11 +242,15 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
         const double rsi = frcp(si), rso = frcp(so);
         const double rzg = frcp(zg), rze = frcp(ze), rzp = frcp(zp), rzq = frcp(zq), rzs = has_s ? frcp(zs) : 0.0;
         const double rzi = frcp(zi), rzo = frcp(zo), rwi = frcp(wi), rwo = frcp(wo);
-        // d = 1 / (z/x [+ w/s] + reg): the proximal term caps d for columns that never approach a bound
-        const double dg = xg * frcp(fma(reg, xg, zg)), de = xe * frcp(fma(reg, xe, ze));
-        const double dp = xp * frcp(fma(reg, xp, zp)), dq = xq * frcp(fma(reg, xq, zq));
-        const double ds = has_s ? xs * frcp(fma(reg, xs, zs)) : 0.0;
-        const double di = frcp(fma(zi, rxi, wi * rsi) + reg), dO = frcp(fma(zo, rxo, wo * rso) + reg);
+        // d = 1 / (z/x [+ w/s] + reg / max(1, x^2)): the proximal term caps d for columns that never approach a bound;
+        // dividing by x^2 for x > 1 keeps it scale invariant (the throughput column grows with the horizon)
+        const double qg = xg > 1.0 ? reg * rxg * rxg : reg, qe = xe > 1.0 ? reg * rxe * rxe : reg;
+        const double qp = xp > 1.0 ? reg * rxp * rxp : reg, qq = xq > 1.0 ? reg * rxq * rxq : reg;
+        const double qs = xs > 1.0 ? reg * rxs * rxs : reg;
+        const double dg = xg * frcp(fma(qg, xg, zg)), de = xe * frcp(fma(qe, xe, ze));
+        const double dp = xp * frcp(fma(qp, xp, zp)), dq = xq * frcp(fma(qq, xq, zq));
+        const double ds = has_s ? xs * frcp(fma(qs, xs, zs)) : 0.0;
+        const double di = frcp(fma(zi, rxi, wi * rsi) + reg), dO = frcp(fma(zo, rxo, wo * rso) + reg);   // x_i, x_o <= u <= 1
         // ---- per-period blocks after eliminating the wind-balance and SoC-bound rows (cancellation-free)
         const double kap = frcp(ds + dl * dl * de + dp);
         const double s11 = ds * (dl * dl * de + dp) * kap;

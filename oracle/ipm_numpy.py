@@ -86,7 +86,7 @@ def solve_batch(A, b, c, u, tol=1e-9, max_iter=60, eta=0.9995, verbose=False, st
             break
         ix = np.flatnonzero(active)
         xa, sa, za, wa, ya = x[ix], s[ix], z[ix], w[ix], y[ix]
-        d = 1.0 / (za / xa + np.where(bd, wa / sa, 0.0) + rho)
+        d = 1.0 / (za / xa + np.where(bd, wa / sa, 0.0) + rho / np.maximum(1.0, xa * xa))
         M = np.einsum("ij,nj,kj->nik", A, d, A, optimize=True)
         M[:, np.arange(m), np.arange(m)] *= (1.0 + 1e-14)
         try:

@@ -184,7 +184,7 @@ class PCR:
         return _mv(self.Dinv, F)[:, :self.T]
 
 
-def solve_batch(lmp, wcf, P, consts, tol=1e-9, feas_tol=1e-9, max_iter=60, eta=0.9995, gap_floor=1e-4, verbose=False, rho=1e-8, start=None, stop_mu=None, start_mode=0):
+def solve_batch(lmp, wcf, P, consts, tol=1e-9, feas_tol=1e-9, max_iter=60, eta=0.9995, gap_floor=1e-4, verbose=False, rho=1e-8, start=None, stop_mu=None, start_mode=0, rho_rule=None, rho_rel=True):
     """lmp [N,T] $/MWh; wcf [N,T] = wind_kw*cf (kW); P [N] battery kW.
     consts: dict(a, binv, half, delta, dur, k_rev) taken from the LP template.
     Returns dict(obj_lp [N] (= c'x, without the design constant), status, iters, g,i,o,s,e [N,T])."""
@@ -266,12 +266,15 @@ def solve_batch(lmp, wcf, P, consts, tol=1e-9, feas_tol=1e-9, max_iter=60, eta=0
             break
         if stop_mu is not None and mu.max() < stop_mu:
             return dict(x=x, z=z, sb=sb, wb=wb, y=y, it=it)
-        # ---- scaling matrix
+        # ---- scaling matrix (rho_rule = (c, lo, hi): proximal weight clip(c*mu, lo, hi) per LP instead of a constant)
+        if rho_rule is not None:
+            rho = np.clip(rho_rule[0] * mu, rho_rule[1], rho_rule[2])[:, None]
         with np.errstate(divide="ignore", invalid="ignore"):
-            d = {k: 1.0 / (z[k] / x[k] + rho) for k in "gepq"}
-            d["s"] = np.where(hs > 0, 1.0 / (np.where(hs > 0, z["s"] / np.where(hs > 0, x["s"], 1.0), 1.0) + rho), 0.0)
+            rr = (lambda k: rho / np.maximum(1.0, x[k] * x[k])) if rho_rel else (lambda k: rho)
+            d = {k: 1.0 / (z[k] / x[k] + rr(k)) for k in "gepq"}
+            d["s"] = np.where(hs > 0, 1.0 / (np.where(hs > 0, z["s"] / np.where(hs > 0, x["s"], 1.0), 1.0) + rr("s")), 0.0)
             for k in "io":
-                d[k] = 1.0 / (z[k] / x[k] + wb[k] / sb[k] + rho)
+                d[k] = 1.0 / (z[k] / x[k] + wb[k] / sb[k] + rr(k))
         # ---- per-period blocks of M after eliminating r4 (pivot m44) and r3 (pivot m33), written in the
         # ---- cancellation-free form  d - d^2/m = d (m - d)/m  (the d's span 20+ orders of magnitude near the end)
         kap = 1.0 / (d["s"] + dl * dl * d["e"] + d["p"])

@@ -338,3 +338,37 @@ def test_design_opt_pem_mode():
     lp0 = L.wind_battery_raw(lmp[0], cf, W, 0.0, pem_mw=355.0, h2_price=2.5, design_opt="PEM")
     pem_ref = np.array([s[1][lp0.meta["Pc"]] for s in sols])
     assert np.allclose(res.sizes["pem_kw"], pem_ref, rtol=1e-4, atol=5.0)
+
+
+def test_full_year_wind_pem_against_the_reference_committed_results():
+    """The CUDA path on the reference's own golden: the 8784-period wind+PEM price-taker LPs of
+    run_pricetaker_wind_PEM.py (batt_mw = 0) against the committed wind_PEM/wind_PEM_RT_1000.csv NPVs.
+    T = 8784 does not fit shared memory: band kernel in global-workspace mode."""
+    import json
+    from pathlib import Path
+    gold = json.load(open(Path(__file__).parent / "golden" / "wind_pem_golden.json"))["wind_PEM_RT_1000"]
+    p = SC.pool()
+    rows = [1, 4, 8]
+    params = {"wind_mw": 847.0, "batt_mw": 0.0, "pem_mw": np.array([gold["pem_mw"][r] for r in rows]),
+              "h2_price_per_kg": np.array([gold["h2_price_per_kg"][r] for r in rows]), "design_opt": False,
+              "extant_wind": True, "wind_resource": np.tile(p["pq1000_rt_cf"], (3, 1)), "DA_LMPs": np.tile(p["pq1000_rt_lmp"], (3, 1))}
+    res = PT.wind_battery_pem_optimize(8784, params)
+    assert (res.status == S.OPTIMAL).all()
+    assert S.last_launch()["smem_bytes"] <= 64                       # workspace mode
+    for k, r in enumerate(rows):
+        assert res.NPV[k] == pytest.approx(gold["NPV"][r], rel=2e-7)
+        assert res.annual_rev_h2[k] == pytest.approx(gold["annual_rev_h2"][r], rel=2e-7)
+
+
+def test_long_horizon_wind_battery_quarter_year():
+    """run_pricetaker_wind_battery.run_design's kind of LP (the reference uses n_time_points = 8736): a 2184-period
+    wind+battery LP against the oracle; the throughput column grows with the horizon (scale-invariant proximal term)."""
+    p = SC.pool()
+    T = 2184
+    lam, cf = p["dalmp_303"][:T], p["dacf_303"][:T]
+    par = {"wind_mw": 847.0, "batt_mw": np.array([84.7, 211.75]), "design_opt": False, "extant_wind": True,
+           "wind_resource": np.tile(cf, (2, 1)), "DA_LMPs": np.tile(lam, (2, 1))}
+    res = PT.wind_battery_optimize(T, par, want_solution=False)
+    assert (res.status == S.OPTIMAL).all() and res.iters.max() <= 60
+    ref = np.array([H.solve(L.wind_battery_raw(lam, cf, 847.0, b))[0] for b in (84.7, 211.75)])
+    assert rel_err(res.obj, ref).max() < REL
