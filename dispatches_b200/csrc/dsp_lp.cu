@@ -463,7 +463,9 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
     *iters_out = it + it0;
 }
 
-template <int BW>
+// WS = true: per-warp work regions in the global workspace P.ws (long horizons); false: in shared memory (the compiler
+// then keeps every W.* access an LDS/STS instead of a generic load)
+template <int BW, bool WS>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) dsp_ipm_band_kernel(const KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -473,8 +475,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) dsp_ipm_band_kernel(const K
         hot = smem + 16;
     }
     const Hot H = hot_views(hot, P);
-    double *base = P.ws ? P.ws + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)P.prob_doubles
-                        : (double *)(smem + P.prob_off) + (size_t)warp * P.prob_doubles;
+    double *base;
+    if (WS) base = P.ws + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)P.prob_doubles;
+    else base = (double *)(smem + P.prob_off) + (size_t)warp * P.prob_doubles;
     Work W;
     const int n = P.n, nb = P.nb, m = P.m;
     W.x = base; W.z = W.x + n; W.c = W.z + n; W.rd = W.c + n; W.d = W.rd + n; W.dx = W.d + n; W.cor = W.dx + n; W.rx = W.cor + n;
@@ -771,11 +774,11 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     CK(cudaMalloc((void **)&T->ticket, 16 * sizeof(unsigned long long)));
     T->dev_allocs.push_back(T->ticket);
     K.prob_doubles = 8 * n + 6 * nb + 3 * m + (m + 2 * wt) + (m + 2 * wt) * (wt + 1);
-    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
-    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
-    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
-    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
-    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaStreamCreateWithFlags(&T->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&T->stream2, cudaStreamNonBlocking));
     *out = T;
@@ -897,11 +900,21 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
     }
     CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
     switch (K.w) {
-        case 1: dsp_ipm_band_kernel<1><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K); break;
-        case 2: dsp_ipm_band_kernel<2><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K); break;
-        case 4: dsp_ipm_band_kernel<4><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K); break;
-        case 8: dsp_ipm_band_kernel<8><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K); break;
-        default: dsp_ipm_band_kernel<16><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K); break;
+        case 1: if (ws_mode) dsp_ipm_band_kernel<1, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else dsp_ipm_band_kernel<1, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                break;
+        case 2: if (ws_mode) dsp_ipm_band_kernel<2, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else dsp_ipm_band_kernel<2, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                break;
+        case 4: if (ws_mode) dsp_ipm_band_kernel<4, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else dsp_ipm_band_kernel<4, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                break;
+        case 8: if (ws_mode) dsp_ipm_band_kernel<8, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else dsp_ipm_band_kernel<8, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                break;
+        default: if (ws_mode) dsp_ipm_band_kernel<16, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                 else dsp_ipm_band_kernel<16, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                 break;
     }
     CK(cudaGetLastError());
     {
