@@ -465,16 +465,18 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
 
 // WS = true: per-warp work regions in the global workspace P.ws (long horizons); false: in shared memory (the compiler
 // then keeps every W.* access an LDS/STS instead of a generic load)
-template <int BW, bool WS>
+// HS = true: the template blob is staged into shared memory (its accesses become LDS too)
+template <int BW, bool WS, bool HS>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) dsp_ipm_band_kernel(const KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned char *hot = P.hot_g;
-    if (P.hot_in_smem) {
+    Hot H;
+    if (HS) {
         tma_stage(smem + 16, P.hot_g, P.hot_bytes, (uint64_t *)smem);
-        hot = smem + 16;
+        H = hot_views(smem + 16, P);
+    } else {
+        H = hot_views(P.hot_g, P);
     }
-    const Hot H = hot_views(hot, P);
     double *base;
     if (WS) base = P.ws + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)P.prob_doubles;
     else base = (double *)(smem + P.prob_off) + (size_t)warp * P.prob_doubles;
@@ -774,11 +776,16 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     CK(cudaMalloc((void **)&T->ticket, 16 * sizeof(unsigned long long)));
     T->dev_allocs.push_back(T->ticket);
     K.prob_doubles = 8 * n + 6 * nb + 3 * m + (m + 2 * wt) + (m + 2 * wt) * (wt + 1);
-    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
-    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
-    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
-    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
-    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaStreamCreateWithFlags(&T->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&T->stream2, cudaStreamNonBlocking));
     *out = T;
@@ -900,20 +907,25 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
     }
     CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
     switch (K.w) {
-        case 1: if (ws_mode) dsp_ipm_band_kernel<1, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
-                else dsp_ipm_band_kernel<1, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+        case 1: if (ws_mode) dsp_ipm_band_kernel<1, true, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else if (hot_in_smem) dsp_ipm_band_kernel<1, false, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else dsp_ipm_band_kernel<1, false, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
                 break;
-        case 2: if (ws_mode) dsp_ipm_band_kernel<2, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
-                else dsp_ipm_band_kernel<2, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+        case 2: if (ws_mode) dsp_ipm_band_kernel<2, true, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else if (hot_in_smem) dsp_ipm_band_kernel<2, false, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else dsp_ipm_band_kernel<2, false, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
                 break;
-        case 4: if (ws_mode) dsp_ipm_band_kernel<4, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
-                else dsp_ipm_band_kernel<4, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+        case 4: if (ws_mode) dsp_ipm_band_kernel<4, true, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else if (hot_in_smem) dsp_ipm_band_kernel<4, false, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else dsp_ipm_band_kernel<4, false, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
                 break;
-        case 8: if (ws_mode) dsp_ipm_band_kernel<8, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
-                else dsp_ipm_band_kernel<8, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+        case 8: if (ws_mode) dsp_ipm_band_kernel<8, true, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else if (hot_in_smem) dsp_ipm_band_kernel<8, false, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else dsp_ipm_band_kernel<8, false, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
                 break;
-        default: if (ws_mode) dsp_ipm_band_kernel<16, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
-                 else dsp_ipm_band_kernel<16, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+        default: if (ws_mode) dsp_ipm_band_kernel<16, true, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                 else if (hot_in_smem) dsp_ipm_band_kernel<16, false, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                else dsp_ipm_band_kernel<16, false, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
                  break;
     }
     CK(cudaGetLastError());
@@ -986,7 +998,9 @@ int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, c
     } else if (K.Pr > 0) {
         dstride = K.Pr;
     }
-    const int nchunk = (int)std::min<int64_t>(in_pinned ? 2 : 8, std::max<int64_t>(1, N / 2048));
+    // templates that run in global-workspace mode share ONE workspace: no concurrent chunk kernels for them
+    const bool ws_template = 16 + (size_t)K.prob_doubles * 8 > (size_t)T->smem_optin;
+    const int nchunk = ws_template ? 1 : (int)std::min<int64_t>(in_pinned ? 2 : 8, std::max<int64_t>(1, N / 2048));
     const int64_t per = (N + nchunk - 1) / nchunk;
     for (int c = 0; c < nchunk; ++c) {
         const int64_t lo = c * per, cnt = std::min<int64_t>(per, N - lo);

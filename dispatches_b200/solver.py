@@ -21,7 +21,6 @@ import os
 
 _LIB_PATH = Path(os.environ.get("DSP_LP_LIB", Path(__file__).resolve().parent / "csrc" / "libdsp_lp.so"))
 _lib = None
-_PINNED_KEEPALIVE = []
 
 OPTIMAL, MAX_ITER, NUMERICAL = 0, 1, 2
 STATUS_NAMES = {OPTIMAL: "optimal", MAX_ITER: "maxIterations", NUMERICAL: "error"}
@@ -242,9 +241,7 @@ class BatchLPSolver:
         """page-locked numpy array (backed by a pinned torch tensor): host buffers the C ABI can DMA from/to directly"""
         import torch
         tt = torch.empty(shape, dtype={np.float64: torch.float64, np.int32: torch.int32}[np.dtype(dtype).type]).pin_memory()
-        a = tt.numpy()
-        _PINNED_KEEPALIVE.append(tt)
-        return a
+        return tt.numpy()          # the array keeps the pinned tensor alive (ndarray.base)
 
     # ------------------------------------------------------------------
     def to_model_space(self, x):

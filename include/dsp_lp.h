@@ -109,7 +109,9 @@ int dsp_lp_solve_batch(const dsp_template *t, int64_t N,
                        void *cuda_stream);
 
 /* Same with HOST pointers: pinned staging, H2D of the parameters, kernel, D2H of the results, one sync.
- * This is the call the Pyomo plugin / sweep drivers make; bench.py's "e2e" number times it.          */
+ * This is the call the Pyomo plugin / sweep drivers make; bench.py's "e2e" number times it.
+ * Page-locked caller buffers are DMA'd directly (no staging copy).  Not re-entrant per template handle: the staging
+ * buffers and streams belong to the handle -- use one handle per host thread.                            */
 int dsp_lp_solve_batch_host(dsp_template *t, int64_t N,
                             const double *cparams, const double *rparams, int64_t rparams_stride,
                             const dsp_opts *opts,
