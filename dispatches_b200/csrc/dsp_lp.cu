@@ -680,6 +680,14 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
             const int cnt = (k <= w) ? D->asm_ptr[i * (w + 1) + k + 1] - D->asm_ptr[i * (w + 1) + k] : 0;
             asm_ptr_pad[i * (wt + 1) + k + 1] = asm_ptr_pad[i * (wt + 1) + k] + cnt;
         }
+    for (int q = 0; q < nasm; ++q)
+        if (D->asm_col[q] < 0 || D->asm_col[q] >= n) { g_err = "asm_col out of range"; return DSP_E_ARG; }
+    for (int q = 0; q < D->cmap.ptr[n]; ++q)
+        if (D->cmap.idx[q] < 0 || D->cmap.idx[q] >= D->Pc) { g_err = "cmap.idx out of range"; return DSP_E_ARG; }
+    for (int q = 0; q < D->bmap.ptr[m]; ++q)
+        if (D->bmap.idx[q] < 0 || D->bmap.idx[q] >= D->Pr) { g_err = "bmap.idx out of range"; return DSP_E_ARG; }
+    for (int q = 0; q < D->umap.ptr[nb]; ++q)
+        if (D->umap.idx[q] < 0 || D->umap.idx[q] >= D->Pr) { g_err = "umap.idx out of range"; return DSP_E_ARG; }
     // CSC of A
     std::vector<int> At_ptr(n + 1, 0), At_idx(nnz);
     std::vector<double> At_val(nnz);

@@ -65,7 +65,7 @@ typedef struct {
     double  feas_tol;     /* relative primal / dual residual tolerance (default 1e-9)   */
     int32_t max_iter;     /* default 60                                                  */
     double  step_frac;    /* fraction of the step to the boundary (default 0.9995)       */
-    int32_t device;       /* CUDA device ordinal, -1 = current                           */
+    int32_t device;       /* reserved (the current CUDA device is used); keep -1        */
     double  reg_primal;   /* proximal regularisation of D^-1 in scaled units (default 1e-8; applied as reg/max(1,x^2)): caps the scaling
                              of never-binding columns (throughput, slacks) so A D A' stays factorisable    */
     int32_t kernel;       /* DSP_KERNEL_AUTO (stage kernel when the template has one), _BAND, _STAGE */
