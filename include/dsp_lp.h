@@ -26,6 +26,9 @@
  * lower band of M = A*diag(d)*A':  M[i][i-k] = sum_{p in asm_ptr[i*(w+1)+k] ..} asm_val[p]*d[asm_col[p]].
  * dispatches_b200/lp_template.py computes all of it.
  *
+ * Size limits: half bandwidth of A*A' <= 16 (padded to 1,2,4,8,16); any m, n -- the per-LP work region lives in shared
+ * memory when it fits (up to ~27 000 doubles) and in a device workspace owned by the template handle otherwise.
+ *
  * All pointers in dsp_lp_solve_batch are DEVICE pointers, the call is stream-ordered and does not
  * synchronise.  dsp_lp_solve_batch_host takes HOST pointers and does the copies itself.
  * Return value: 0 on success, a negative DSP_E_* code on argument / launch errors.  Per-problem outcome
