@@ -133,19 +133,14 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    # CPU baseline first: the process pool must be forked before CUDA is initialised in this process
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        lmp0, cf0, W0, P0, _ = workload(0)
-        cores = host_cores()
-        n_sample = int(min(BATCH, max(500, 400 * cores)))
-        cpu_reference_run(lmp0, cf0, W0, P0, min(n_sample, 16 * cores))          # warm-up (imports, page-in)
-        ref, dt, procs = cpu_reference_run(lmp0, cf0, W0, P0, n_sample)
-        cpu = dict(ref=ref, dt=dt, procs=procs, n=n_sample)
-
     import torch
     import torch.distributed as dist
     from dispatches_b200 import solver as S, templates as TP
@@ -233,9 +228,11 @@ def main():
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
         dist.all_reduce(s2, op=dist.ReduceOp.MAX)
         stats[2] = s2[2]
+    stats = stats.cpu()
+    if world > 1:                              # all collectives are done: every rank leaves the group together
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     total = BATCH * world
     value = total * args.steps / (step_ms * 1e-3)
@@ -275,15 +272,29 @@ def main():
             "solver": {"non_optimal": int(stats[0]), "iters_mean": float(stats[1]) / total, "iters_max": int(stats[2]),
                        "launch": S.last_launch()},
             "clocks": clocks, "wall_s_timed_loop": t_wall}
+    if not args.no_cpu_baseline:
+        # CPU baseline in a fresh interpreter (no fork of this CUDA process; nothing runs before the ranks rendezvous)
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            outp = os.path.join(td, "cpu.npz")
+            code = ("import sys; sys.path.insert(0, %r); import numpy as np, bench; "
+                    "lmp, cf, W, P, _ = bench.workload(0); c = bench.host_cores(); n = int(min(bench.BATCH, max(500, 400 * c))); "
+                    "bench.cpu_reference_run(lmp, cf, W, P, min(n, 16 * c)); ref, dt, procs = bench.cpu_reference_run(lmp, cf, W, P, n); "
+                    "np.savez(%r, ref=ref, dt=dt, procs=procs, n=n)") % (str(ROOT), outp)
+            rc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+            if rc.returncode == 0:
+                z = np.load(outp)
+                cpu = dict(ref=z["ref"], dt=float(z["dt"]), procs=int(z["procs"]), n=int(z["n"]))
+            else:
+                line["cpu_baseline"] = {"error": rc.stderr[-300:]}
     if cpu is not None:
         ref, dt, procs, n_sample = cpu["ref"], cpu["dt"], cpu["procs"], cpu["n"]
         err = np.abs(r_host.obj[:n_sample] - ref) / np.maximum(1.0, np.abs(ref))
         line["cpu_baseline"] = {"value": n_sample / dt, "unit": "LPs/s", "cores": procs, "kind": "port",
                                 "sample": f"first {n_sample} LPs of rank 0's batch, restated LP + HiGHS dual simplex, {procs} processes"}
         line["max_rel_err_vs_oracle"] = float(err.max())
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":

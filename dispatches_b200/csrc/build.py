@@ -36,6 +36,18 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Builds the library if sources are newer.  Serialised across processes with a file lock: under torchrun every rank
+    calls this at start-up and only the first one may run nvcc."""
+    import fcntl
+    with open(HERE / ".build.lock", "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     if not force and not needs_build():
         return LIB
     cmd = [nvcc_path(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), *map(str, SOURCES), "-o", str(LIB)]

@@ -1,0 +1,377 @@
+"""Double-loop (bidding / tracking) LPs on the batched CUDA solver -- SURVEY.md §8(f)-2.
+
+Host-side mirror of the reference's ``MultiPeriodWindBattery`` (case_studies/renewables_case/
+wind_battery_double_loop.py:104-352) and of the three IDAES objects that own its LPs in the reference's tests
+(case_studies/renewables_case/tests/test_multiperiod_wind_battery_doubleloop.py:47-111, :114-175, :178-252):
+``Tracker``, ``SelfScheduler`` / ``Bidder`` and the ``Backcaster`` price forecaster.  idaes-pse is not vendored in the
+reference; the formulation of those objects is restated (see oracle/double_loop.py for the anchoring on the
+reference's known answers) and only the part of their interface the reference exercises is provided.
+
+Same names and argument meaning as the reference; the one extension is batching: ``wind_capacity_factors`` may be
+[N, L] and the sizes [N] (N independent simulations advanced in lock step -- the reference runs one per process), and
+``market_dispatch`` / price histories may carry a leading batch axis.  Every LP goes through
+``BatchLPSolver.solve_host`` (C-ABI ``dsp_lp_solve_batch_host``); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import dataclasses
+from collections import deque
+
+import numpy as np
+
+from . import templates as TP
+from .solver import BatchLPSolver, OPTIMAL
+
+_SOLVERS = {}
+
+
+def _lp_solve(mode, T, cparams, rparams, n_tracking_hour=1, options=None):
+    """One batched solve of the operation template; returns (obj [N], status [N], columns {name: [N,T]})."""
+    key = (mode, T, n_tracking_hour, tuple(sorted((options or {}).items())))
+    if key not in _SOLVERS:
+        _SOLVERS[key] = BatchLPSolver(TP.wind_battery_operation(T, mode, n_tracking_hour), **(options or {}))
+    sol = _SOLVERS[key]
+    r = sol.solve_host(np.ascontiguousarray(cparams), np.ascontiguousarray(rparams), want_x=True)
+    return r.obj, r.status, _columns(sol.t, sol.to_model_space(r.x), T)
+
+
+_COLS = dict(grid="blk[{t}].fs.splitter.grid_elec[0]", batt_in="blk[{t}].fs.battery.elec_in[0]",
+             batt_out="blk[{t}].fs.battery.elec_out[0]", soc="blk[{t}].fs.battery.state_of_charge[0]",
+             throughput="blk[{t}].fs.battery.energy_throughput[0]", waste="wind_waste_kw[{t}]",
+             under="power_underdelivered_kw[{t}]", over="power_overdelivered_kw[{t}]",
+             da="day_ahead_power_kw[{t}]", underbid="real_time_underbid_power_kw[{t}]")
+
+
+def _columns(template, xm, T):
+    cn = {n: j for j, n in enumerate(template.col_names)}
+    out = {}
+    for k, pat in _COLS.items():
+        if pat.format(t=0) in cn:
+            out[k] = xm[:, [cn[pat.format(t=t)] for t in range(T)]]
+    return out
+
+
+# ---- minimal stand-ins for idaes.apps.grid_integration.model_data (only the fields the reference's tests set)
+@dataclasses.dataclass
+class RenewableGeneratorModelData:
+    gen_name: str
+    bus: str
+    p_min: float
+    p_max: float
+    p_cost: float = 0.0
+    fixed_commitment: object = None
+    generator_type = "renewable"
+
+
+@dataclasses.dataclass
+class ThermalGeneratorModelData:
+    gen_name: str
+    bus: str
+    p_min: float
+    p_max: float
+    min_down_time: float = 0
+    min_up_time: float = 0
+    ramp_up_60min: float = 0
+    ramp_down_60min: float = 0
+    shutdown_capacity: float = 0
+    startup_capacity: float = 0
+    initial_status: int = 1
+    initial_p_output: float = 0
+    production_cost_bid_pairs: list = None
+    include_default_p_cost: bool = False
+    startup_cost_pairs: list = None
+    fixed_commitment: object = None
+    generator_type = "thermal"
+
+
+class Backcaster:
+    """Price forecaster: scenario k replays the historical days in reverse chronological order starting k days back
+    (pinned by the reference's 48-h known bids for k = 0, test_multiperiod_wind_battery_doubleloop.py:124-129,168-175)."""
+
+    def __init__(self, historical_da_prices, historical_rt_prices, max_historical_days=10):
+        self._da = {b: list(np.asarray(v, float)) for b, v in historical_da_prices.items()}
+        self._rt = {b: list(np.asarray(v, float)) for b, v in historical_rt_prices.items()}
+        for hist in (self._da, self._rt):
+            for b, v in hist.items():
+                if len(v) < 24:
+                    raise ValueError(f"At least a day of the historical prices for bus {b} is required.")
+        self.max_historical_days = max_historical_days
+
+    @staticmethod
+    def _forecast(hist, hour, horizon, n_samples):
+        h = np.asarray(hist, float)
+        days = h[: (h.size // 24) * 24].reshape(-1, 24)
+        nd = days.shape[0]
+        reps = (hour + horizon) // 24 + 1
+        return np.array([np.concatenate([days[(nd - 1 - k - r) % nd] for r in range(reps)])[hour:hour + horizon]
+                         for k in range(n_samples)])
+
+    def forecast_day_ahead_prices(self, date, hour, bus, horizon, n_samples):
+        return self._forecast(self._da[bus], hour, horizon, n_samples)
+
+    def forecast_real_time_prices(self, date, hour, bus, horizon, n_samples):
+        return self._forecast(self._rt[bus], hour, horizon, n_samples)
+
+    def forecast_day_ahead_and_real_time_prices(self, date, hour, bus, horizon, n_samples):
+        return (self.forecast_day_ahead_prices(date, hour, bus, horizon, n_samples),
+                self.forecast_real_time_prices(date, hour, bus, horizon, n_samples))
+
+    def fetch_hourly_stats_from_prescient(self, *a, **k):       # bookkeeping hook of the co-simulation; nothing to solve
+        raise NotImplementedError("Prescient co-simulation is outside the hot path (SURVEY.md §8)")
+
+
+class _Block:
+    """What ``populate_model`` fills: the state the reference keeps on a Pyomo block (sizes live on the model object)."""
+    def __init__(self):
+        self.horizon = 0
+        self._time_idx = 0
+        self.soc0 = None            # [N] kWh
+        self.thr0 = None            # [N] kWh
+        self.cf = None              # [N, horizon]
+        self.wind_waste_penalty = 1e3          # wind_battery_double_loop.py:165
+        self.sol = None             # columns of the last solve, kW / kWh, each [N, horizon]
+        self.P_T = None             # [N, horizon] MW
+        self.tot_cost = None        # [N, horizon] $
+        self.wind_waste = None      # [N, horizon] MW
+
+
+class MultiPeriodWindBattery:
+    """wind_battery_double_loop.py:104-352.  ``wind_capacity_factors`` [L] or [N, L]; sizes scalar or [N]."""
+
+    def __init__(self, model_data, wind_capacity_factors=None, wind_pmax_mw=200.0, battery_pmax_mw=25.0,
+                 battery_energy_capacity_mwh=100.0):
+        self.model_data = model_data
+        if wind_capacity_factors is None:
+            raise ValueError("Please provide wind capacity factors.")       # :130-131
+        self._wind_capacity_factors = np.atleast_2d(np.asarray(wind_capacity_factors, float))
+        N = self._wind_capacity_factors.shape[0]
+        sizes = np.broadcast_arrays(np.zeros(N), wind_pmax_mw, battery_pmax_mw, battery_energy_capacity_mwh)
+        self.N = sizes[0].shape[0]
+        if N == 1 and self.N > 1:
+            self._wind_capacity_factors = np.repeat(self._wind_capacity_factors, self.N, axis=0)
+        self._wind_pmax_mw, self._battery_pmax_mw, self._battery_energy_capacity_mwh = (np.array(s, float) for s in sizes[1:])
+        self.result_list = []
+
+    # -- populate / update (:141-206)
+    def populate_model(self, b, horizon):
+        b.horizon = horizon
+        b._time_idx = 0
+        b.soc0 = np.zeros(self.N)          # initial_state_of_charge fixed at its initial value 0 (:76-77)
+        b.thr0 = np.zeros(self.N)          # initial_energy_throughput: free until the first update; 0 is optimal
+        b.cf = self._wind_capacity_factors[:, 0:horizon].copy()
+        return b
+
+    def update_model(self, b, realized_soc, realized_energy_throughput):
+        """realized_* : sequences (deque) of per-hour values, each a scalar or [N] (kWh)."""
+        b.soc0 = np.round(np.broadcast_to(np.asarray(realized_soc[-1], float), (self.N,)), 2)               # :189-191
+        b.thr0 = np.round(np.broadcast_to(np.asarray(realized_energy_throughput[-1], float), (self.N,)), 2)  # :193-196
+        b._time_idx = b._time_idx + min(len(realized_soc), 24)                                                # :199-200
+        b.cf = self._get_capacity_factors(b)
+
+    def _get_capacity_factors(self, b):
+        L = self._wind_capacity_factors.shape[1]
+        ans = self._wind_capacity_factors[:, b._time_idx:b._time_idx + b.horizon]
+        if ans.shape[1] < b.horizon:                                                                          # :222-223
+            ans = np.concatenate([ans, self._wind_capacity_factors[:, 0:b.horizon - ans.shape[1]]], axis=1)
+        return ans
+
+    # -- rparams / post-processing shared by the tracker and the bidders
+    def _rparams(self, b, signal_mw=None):
+        return TP.wind_battery_operation_rparams(b.horizon, b.cf, self._wind_pmax_mw, self._battery_pmax_mw,
+                                                 self._battery_energy_capacity_mwh, b.soc0, b.thr0, signal_mw)
+
+    def _load_solution(self, b, cols):
+        b.sol = cols
+        b.P_T = (cols["grid"] + cols["batt_out"]) * 1e-3                                                      # :168
+        b.wind_waste = cols["waste"] * 1e-3                                                                   # :169
+        prev = np.concatenate([b.thr0[:, None], cols["throughput"][:, :-1]], axis=1)
+        kdeg = TP.DEGRADATION * TP.BATT_REP_COST_KWH
+        b.tot_cost = (self._wind_pmax_mw[:, None] * 1e3 * TP.WIND_OP_COST / 8760.0 + kdeg * (cols["throughput"] - prev)
+                      + b.wind_waste_penalty * b.wind_waste)                                                  # :170-171
+
+    @staticmethod
+    def get_last_delivered_power(b, last_implemented_time_step):
+        return b.P_T[:, last_implemented_time_step]                                                           # :239-240
+
+    @staticmethod
+    def get_implemented_profile(b, last_implemented_time_step):
+        n = last_implemented_time_step + 1
+        return {"realized_soc": deque(b.sol["soc"][:, t] for t in range(n)),                                  # :257-270
+                "realized_energy_throughput": deque(b.sol["throughput"][:, t] for t in range(n))}
+
+    def record_results(self, b, date=None, hour=None, **kwargs):
+        """Rows of the reference's result table (:272-335), one per (simulation, horizon hour)."""
+        import pandas as pd
+        rows = []
+        wind_gen = (b.sol["grid"] + b.sol["batt_in"]) * 1e-3
+        for k in range(self.N):
+            for t in range(b.horizon):
+                row = {"Generator": self.model_data.gen_name, "Date": date, "Hour": hour, "Horizon [hr]": int(t),
+                       "Total Wind Generation [MW]": round(float(wind_gen[k, t]), 2),
+                       "Total Power Output [MW]": round(float(b.P_T[k, t]), 2),
+                       "Wind Power Output [MW]": round(float(b.sol["grid"][k, t] * 1e-3), 2),
+                       "Wind Curtailment [MW]": round(float(b.wind_waste[k, 0]), 2),        # the reference reads index 0 (:309)
+                       "Battery Power Output [MW]": round(float(b.sol["batt_out"][k, t] * 1e-3), 2),
+                       "Wind Power to Battery [MW]": round(float(b.sol["batt_in"][k, t] * 1e-3), 2),
+                       "State of Charge [MWh]": round(float(b.sol["soc"][k, t] * 1e-3), 2),
+                       "Total Cost [$]": round(float(b.tot_cost[k, t]), 2)}
+                if self.N > 1:
+                    row["Simulation"] = k
+                row.update(kwargs)
+                rows.append(row)
+        self.result_list.append(pd.DataFrame(rows))
+
+    def write_results(self, path):
+        import pandas as pd
+        pd.concat(self.result_list).to_csv(path, index=False)                                                  # :344
+
+    @property
+    def power_output(self):
+        return "P_T"
+
+    @property
+    def total_cost(self):
+        return ("tot_cost", 1)
+
+
+class Tracker:
+    """idaes Tracker as the reference drives it (test_multiperiod_wind_battery_doubleloop.py:68-87): one LP per call of
+    ``track_market_dispatch`` over ``tracking_horizon`` hours, the first ``n_tracking_hour`` tracked hard."""
+
+    def __init__(self, tracking_model_object, tracking_horizon, n_tracking_hour, solver=None):
+        self.tracking_model_object = tracking_model_object
+        self.tracking_horizon, self.n_tracking_hour = int(tracking_horizon), int(n_tracking_hour)
+        self.solver_options = dict(solver or {})
+        self.fs = _Block()
+        tracking_model_object.populate_model(self.fs, self.tracking_horizon)
+        self.daily_stats, self.projection, self.result_list = None, None, []
+        self.status = None
+
+    @property
+    def power_output(self):
+        return self.fs.P_T
+
+    def track_market_dispatch(self, market_dispatch, date, hour):
+        obj_ = self.tracking_model_object
+        N, H = obj_.N, self.tracking_horizon
+        md = np.broadcast_to(np.atleast_2d(np.asarray(market_dispatch, float)), (N, H))
+        obj, status, cols = _lp_solve("tracker", H, np.full((N, 1), self.fs.wind_waste_penalty), obj_._rparams(self.fs, md),
+                                      self.n_tracking_hour, self.solver_options)
+        self.status = status
+        if np.any(status != OPTIMAL):
+            raise RuntimeError(f"tracking LP not optimal for simulations {np.nonzero(status != OPTIMAL)[0][:8].tolist()}")
+        obj_._load_solution(self.fs, cols)
+        self.objective = obj
+        self.power_underdelivered, self.power_overdelivered = cols["under"] * 1e-3, cols["over"] * 1e-3
+        obj_.record_results(self.fs, date=date, hour=hour)
+        last = self.n_tracking_hour - 1
+        profiles = obj_.get_implemented_profile(self.fs, last)
+        self._last_delivered = obj_.get_last_delivered_power(self.fs, last).copy()
+        obj_.update_model(self.fs, **profiles)
+        return profiles
+
+    def get_last_delivered_power(self):
+        return self._last_delivered
+
+
+class _StochasticProgramBidder:
+    def __init__(self, bidding_model_object, day_ahead_horizon, real_time_horizon, n_scenario, solver=None, forecaster=None):
+        if n_scenario != 1:
+            raise NotImplementedError("n_scenario > 1 couples the scenario blocks (non-anticipativity rows): not batched yet")
+        self.bidding_model_object = bidding_model_object
+        self.day_ahead_horizon, self.real_time_horizon = int(day_ahead_horizon), int(real_time_horizon)
+        self.n_scenario, self.forecaster = n_scenario, forecaster
+        self.solver_options = dict(solver or {})
+        self.generator = bidding_model_object.model_data.gen_name
+        self.day_ahead_model, self.real_time_model = _Block(), _Block()
+        bidding_model_object.populate_model(self.day_ahead_model, self.day_ahead_horizon)
+        bidding_model_object.populate_model(self.real_time_model, self.real_time_horizon)
+        self.bids_result_list = []
+
+    def _forecasts(self, which, date, hour, horizon):
+        """[N, horizon] forecast prices; a forecaster per simulation may be given as a list."""
+        N = self.bidding_model_object.N
+        fcs = self.forecaster if isinstance(self.forecaster, (list, tuple)) else [self.forecaster] * N
+        bus = self.bidding_model_object.model_data.bus
+        out = np.array([getattr(f, which)(date=date, hour=hour, bus=bus, horizon=horizon, n_samples=1)[0] for f in fcs])
+        return out
+
+    def _solve(self, blk, mode, da, rt, da_dispatch=None):
+        obj_ = self.bidding_model_object
+        N, H = obj_.N, blk.horizon
+        cp = np.concatenate([da, rt, np.full((N, 1), blk.wind_waste_penalty)], axis=1)
+        obj, status, cols = _lp_solve(mode, H, cp, obj_._rparams(blk, da_dispatch), 1, self.solver_options)
+        if np.any(status != OPTIMAL):
+            raise RuntimeError(f"bidding LP not optimal for simulations {np.nonzero(status != OPTIMAL)[0][:8].tolist()}")
+        obj_._load_solution(blk, cols)
+        if da_dispatch is not None:                      # constant dropped from the template (bilinear in the parameters)
+            obj = obj - np.sum((da - rt) * da_dispatch, axis=1)
+        blk.objective = -obj                             # the IDAES objective is a maximisation
+        return cols
+
+    def compute_day_ahead_bids(self, date, hour=0):
+        H = self.day_ahead_horizon
+        da = self._forecasts("forecast_day_ahead_prices", date, hour, H)
+        rt = self._forecasts("forecast_real_time_prices", date, hour, H)
+        cols = self._solve(self.day_ahead_model, "bidder_da", da, rt)
+        self.day_ahead_power = cols["da"] * 1e-3                       # [N, H] MW
+        bids = self._assemble_bids(self.day_ahead_power, da, hour)
+        self.bidding_model_object.record_results(self.day_ahead_model, date=date, hour=hour, market="Day-ahead")
+        return bids
+
+    def compute_real_time_bids(self, date, hour, realized_day_ahead_prices, realized_day_ahead_dispatches):
+        H = self.real_time_horizon
+        N = self.bidding_model_object.N
+
+        def window(a):                                                  # hours past the end repeat the last value
+            a = np.broadcast_to(np.atleast_2d(np.asarray(a, float)), (N, np.shape(a)[-1]))
+            idx = np.minimum(np.arange(hour, hour + H), a.shape[1] - 1)
+            return a[:, idx]
+        da, disp = window(realized_day_ahead_prices), window(realized_day_ahead_dispatches)
+        rt = self._forecasts("forecast_real_time_prices", date, hour, H)
+        cols = self._solve(self.real_time_model, "bidder_rt", da, rt, disp)
+        self.real_time_underbid_power = cols["underbid"] * 1e-3
+        bids = self._assemble_bids(self.real_time_model.P_T, rt, hour)
+        self.bidding_model_object.record_results(self.real_time_model, date=date, hour=hour, market="Real-time")
+        return bids
+
+    def update_day_ahead_model(self, **profiles):
+        self.bidding_model_object.update_model(self.day_ahead_model, **profiles)
+
+    def update_real_time_model(self, **profiles):
+        self.bidding_model_object.update_model(self.real_time_model, **profiles)
+
+    @staticmethod
+    def _scalar(a):
+        a = np.asarray(a)
+        return float(a[0]) if a.size == 1 else a
+
+
+class SelfScheduler(_StochasticProgramBidder):
+    """Self-schedule bids: p_max[t] = the scheduled power, rounded to 4 decimals
+    (the reference reads ``bids[t][gen]['p_max']``, test_multiperiod_wind_battery_doubleloop.py:154-156)."""
+
+    def _assemble_bids(self, power_mw, prices, hour):
+        md = self.bidding_model_object.model_data
+        bids = {}
+        for t in range(power_mw.shape[1]):
+            p = np.round(power_mw[:, t], 4)
+            bids[t + hour] = {self.generator: {"p_min": md.p_min, "p_max": self._scalar(p), "p_min_agc": md.p_min,
+                                               "p_max_agc": self._scalar(p), "p_cost": getattr(md, "p_cost", 0.0)}}
+        return bids
+
+
+class Bidder(_StochasticProgramBidder):
+    """Price-quantity bids of a thermal-type participant: per hour the curve [(p_min, 0), (P, P*price)] built from the
+    scenario's (power, price) pair (the reference reads ``bids[t][gen]['p_cost'][-1][1]``, :233-236)."""
+
+    def _assemble_bids(self, power_mw, prices, hour):
+        md = self.bidding_model_object.model_data
+        bids = {}
+        for t in range(power_mw.shape[1]):
+            p = np.round(np.maximum(power_mw[:, t], md.p_min), 4)
+            cost = np.round(np.round(prices[:, t], 4) * (p - md.p_min), 4)
+            curve = [(md.p_min, 0.0), (self._scalar(p), self._scalar(cost))]
+            bids[t + hour] = {self.generator: {"p_cost": curve, "p_min": md.p_min, "p_max": self._scalar(p),
+                                               "startup_capacity": md.p_min, "shutdown_capacity": md.p_min}}
+        return bids

@@ -287,3 +287,85 @@ def fossil_surrogate(T: int = 168, par=None) -> LPTemplate:
             B.le(f"ramp_down[{t}]", {pw[t]: -1.0}, P["ramp"] - P["pprev0"])
     B.meta.update(kind="fossil_surrogate", T=T)
     return B.build(equilibrate=True)          # salt inventories (1e6 kg) next to powers (1e2 MW): must equilibrate
+
+
+# --------------------------------------------------------------------------------------
+# double-loop operation model: tracking / bidding LPs
+# --------------------------------------------------------------------------------------
+BATT_REP_COST_KWH = BATT_CAP_COST_KW * 0.5 / 4.0     # load_parameters.py:48
+LARGE_PENALTY = 1e4                                  # idaes-pse 2.0 Tracker deviation / Bidder underbid penalty
+
+
+def wind_battery_operation(T: int, mode: str, n_tracking_hour: int = 1) -> LPTemplate:
+    """Operation model of wind_battery_double_loop.py:27-83,160-171 (sizes fixed, initial SoC / throughput fixed, no
+    periodic row) with the objective and extra rows of the IDAES double-loop object that owns it:
+
+      mode "tracker"    Tracker.track_market_dispatch: min tot_cost + pen_t (under_t + over_t),
+                        P_T[t] + under_t == dispatch_t + over_t
+      mode "bidder_da"  SelfScheduler / Bidder day-ahead problem (one scenario): max da*Pda + rt*(P_T - Pda) - tot_cost,
+                        Pda_t <= P_T[t]
+      mode "bidder_rt"  the real-time problem: Pda fixed to the cleared day-ahead dispatch, underbid_t >= 0 at 1e4 $/MW
+                        (the constant (da-rt)*Pda is added back by the host, dispatches_b200/double_loop.py)
+
+    Internal columns are in kW (the reference's unit for the block Vars); the MW quantities of the IDAES layer
+    (under/over, day_ahead_power, underbid) are carried in kW too and scaled on read-back.
+    rparams = [wind_kw*cf_t (T), batt_kw, energy_kwh, soc0_kwh, thr0_kwh, wind_kw, dispatch_or_da_dispatch_MW_t (T)]
+    cparams = tracker: [wind_waste_penalty];  bidder_*: [da_t (T), rt_t (T), wind_waste_penalty]   ($/MWh, $/MW)
+    """
+    assert mode in ("tracker", "bidder_da", "bidder_rt")
+    iP, iE, iS0, iE0, iW, iD = T, T + 1, T + 2, T + 3, T + 4, T + 5
+    Pc = 1 if mode == "tracker" else 2 * T + 1
+    iPen = Pc - 1
+    B = TemplateBuilder(f"wind_battery_{mode}_T{T}", Pc=Pc, Pr=2 * T + 5)
+    kdeg = DEGRADATION * BATT_REP_COST_KWH
+    g, i, o, s, e, waste = {}, {}, {}, {}, {}, {}
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        g[t] = B.var(p + "splitter.grid_elec[0]")
+        i[t] = B.var(p + "battery.elec_in[0]", ub=(0.0, {iP: 1.0}))           # battery.py:159-161
+        o[t] = B.var(p + "battery.elec_out[0]", ub=(0.0, {iP: 1.0}))          # battery.py:163-165
+        s[t] = B.var(p + "battery.state_of_charge[0]")
+        e[t] = B.var(p + "battery.energy_throughput[0]")
+        waste[t] = B.var(f"wind_waste_kw[{t}]")                               # double_loop.py:169
+        B.cost(waste[t], (0.0, {iPen: 1e-3}))                                 # :165,171
+    B.cost(e[T - 1], kdeg)                                                    # sum_t var_cost telescopes (wind_battery_LMP.py:67-70)
+    B.obj_const((0.0, {iE0: -kdeg, iW: T * WIND_OP_COST / 8760.0}))           # :61-64
+    for t in range(T):
+        row = {s[t]: 1.0, i[t]: -ETA_C, o[t]: 1.0 / ETA_D}                     # battery.py:145-149
+        if t > 0:
+            row[s[t - 1]] = -1.0
+        B.eq(f"soc[{t}]", row, (0.0, {iS0: 1.0}) if t == 0 else 0.0)          # double_loop.py:76-77,190-191
+        row = {e[t]: 1.0, i[t]: -0.5, o[t]: -0.5}                              # battery.py:151-153
+        if t > 0:
+            row[e[t - 1]] = -1.0
+        B.eq(f"throughput[{t}]", row, (0.0, {iE0: 1.0}) if t == 0 else 0.0)   # double_loop.py:193-196
+        B.le(f"soc_bound[{t}]", {s[t]: 1.0, e[t]: DEGRADATION}, (0.0, {iE: 1.0}))    # battery.py:155-157
+        B.eq(f"wind[{t}]", {g[t]: 1.0, i[t]: 1.0, waste[t]: 1.0}, (0.0, {t: 1.0}))   # wind_power.py:120-122 + splitter
+        if mode == "tracker":
+            un = B.var(f"power_underdelivered_kw[{t}]"); ov = B.var(f"power_overdelivered_kw[{t}]")
+            pen = LARGE_PENALTY if t < n_tracking_hour else LARGE_PENALTY / max(1, T - n_tracking_hour)
+            B.cost(un, pen * 1e-3); B.cost(ov, pen * 1e-3)
+            B.eq(f"tracking_dispatch[{t}]", {g[t]: 1.0, o[t]: 1.0, un: 1.0, ov: -1.0}, (0.0, {iD + t: 1e3}))
+        else:
+            B.cost(g[t], (0.0, {T + t: -1e-3})); B.cost(o[t], (0.0, {T + t: -1e-3}))
+            if mode == "bidder_da":
+                da = B.var(f"day_ahead_power_kw[{t}]")
+                B.cost(da, (0.0, {t: -1e-3, T + t: 1e-3}))
+                B.le(f"day_ahead_power_ub[{t}]", {da: 1.0, g[t]: -1.0, o[t]: -1.0})
+            else:
+                ub = B.var(f"real_time_underbid_power_kw[{t}]"); sp_ = B.var(f"surplus_kw[{t}]")
+                B.cost(ub, LARGE_PENALTY * 1e-3)
+                B.eq(f"day_ahead_power_ub[{t}]", {g[t]: 1.0, o[t]: 1.0, ub: 1.0, sp_: -1.0}, (0.0, {iD + t: 1e3}))
+    B.meta.update(kind="wind_battery_operation", mode=mode, T=T, n_tracking_hour=n_tracking_hour)
+    return B.build()
+
+
+def wind_battery_operation_rparams(T, cf, wind_mw, batt_mw, energy_mwh, soc0_kwh=0.0, thr0_kwh=0.0, signal_mw=None):
+    """rparams rows of wind_battery_operation: cf [N,T] or [T]; the rest scalar or [N]; signal_mw [N,T] / [T] / None."""
+    cf = np.atleast_2d(np.asarray(cf, float))
+    N = cf.shape[0]
+    col = lambda v, k=1.0: np.broadcast_to(np.asarray(v, float) * k, (N,))[:, None]
+    W = col(wind_mw, 1e3)
+    sig = np.zeros((N, T)) if signal_mw is None else np.broadcast_to(np.atleast_2d(np.asarray(signal_mw, float)), (N, T))
+    return np.ascontiguousarray(np.concatenate(
+        [cf * W, col(batt_mw, 1e3), col(energy_mwh, 1e3), col(soc0_kwh), col(thr0_kwh), W, sig], axis=1))

@@ -15,8 +15,13 @@ Writes
                            price / capacity-factor series they were computed on go into lmp_pool.npz as pq1000_* / pq500_*).
   unit_kats.json        -- known answers of the reference's unit-model tests for the battery rows
                            (unit_models/tests/test_battery.py:40-67, :95-119).
+  double_loop_golden.json -- inputs and known answers of the reference's double-loop tests
+                           (case_studies/renewables_case/tests/test_multiperiod_wind_battery_doubleloop.py:78-111 tracker,
+                           :168-175 self-schedule bids, :245-252 thermal-generator bid prices): the first 48 h of
+                           309_WIND_1-RTCF / 309_DALMP / 309_RTLMP and the asserted vectors (read with ``ast``).
 No reference SOURCE is copied: only numeric data and test constants.
 """
+import ast
 import json
 from pathlib import Path
 
@@ -27,7 +32,33 @@ REF = Path("/root/reference/dispatches")
 OUT = Path(__file__).parent
 
 
+def double_loop():
+    rc = REF / "case_studies" / "renewables_case"
+    df = pd.read_csv(rc / "data" / "Wind_Thermal_Dispatch.csv")
+    tree = ast.parse(open(rc / "tests" / "test_multiperiod_wind_battery_doubleloop.py").read())
+    lists = {}
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.Assign) and isinstance(node.targets[0], ast.Name) and isinstance(node.value, ast.List):
+                try:
+                    lists[fn.name, node.targets[0].id] = [float(v) for v in ast.literal_eval(node.value)]
+                except (ValueError, TypeError):
+                    pass
+    gold = dict(
+        cf_309_rt=df["309_WIND_1-RTCF"].values[:48].tolist(),
+        da_309=df["309_DALMP"].values[:48].tolist(), rt_309=df["309_RTLMP"].values[:48].tolist(),
+        wind_pmax_mw=200.0, battery_pmax_mw=25.0, battery_energy_capacity_mwh=100.0,
+        tracker=dict(market_dispatch=lists["test_track_market_dispatch", "market_dispatch"],
+                     expected_wind_power=lists["test_track_market_dispatch", "expected_wind_power"],
+                     rel=1e-3, abs_power=1e-3, tracking_horizon=4, n_tracking_hour=1),
+        self_schedule=dict(known_solution=lists["test_compute_bids_self_schedule", "known_solution"], reltol=1e-2,
+                           day_ahead_horizon=48, n_scenario=1),
+        thermal_bid=dict(known_solution=lists["test_compute_bids_thermal_gen", "known_solution"], reltol=1e-2))
+    json.dump(gold, open(OUT / "double_loop_golden.json", "w"))
+
+
 def main():
+    double_loop()
     rc = REF / "case_studies" / "renewables_case"
     df = pd.read_csv(rc / "data" / "Wind_Thermal_Dispatch.csv")
     assert len(df) == 8736
@@ -74,4 +105,5 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    double_loop() if sys.argv[1:] == ["double_loop"] else main()
