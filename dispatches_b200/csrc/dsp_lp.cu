@@ -511,7 +511,12 @@ namespace {
 #ifndef DSP_STAGE_WPB
 #define DSP_STAGE_WPB 4
 #endif
-__global__ void __launch_bounds__(32 * DSP_STAGE_WPB, DSP_STAGE_MINB) dsp_ipm_stage_wb_kernel(const KParams P, const stagewb::StageParams S) {
+#ifdef DSP_STAGE_MAXNREG
+__global__ void __maxnreg__(DSP_STAGE_MAXNREG) dsp_ipm_stage_wb_kernel(
+#else
+__global__ void __launch_bounds__(32 * DSP_STAGE_WPB, DSP_STAGE_MINB) dsp_ipm_stage_wb_kernel(
+#endif
+        const KParams P, const stagewb::StageParams S) {
     const int lane = threadIdx.x & 31;
     stagewb::Out O;
     O.obj = P.obj; O.x_out = P.x_out; O.y_out = P.y_out; O.status = P.status; O.iters = P.iters; O.n = P.n; O.m = P.m;

@@ -70,6 +70,10 @@ __device__ __forceinline__ double wsum(double v) {
     return v;
 }
 
+#ifndef DSP_STAGE_KU
+#define DSP_STAGE_KU 16
+#endif
+
 struct Sym2 { double a, b, c; };            // [[a, b], [b, c]]
 struct Mat2 { double a, b, c, d; };         // [[a, b], [c, d]]
 
@@ -107,7 +111,7 @@ struct Factor {          // per-lane pieces of the twisted block LDL'
 // backward half of the solve: on entry (g1, g2) is the forward-eliminated right-hand side, on exit the solution
 template <int TT>
 __device__ __forceinline__ void tw_back(const Factor &F, double &g1, double &g2, int T, int lane) {
-    constexpr int KU = TT > 0 ? 16 : 1;
+    constexpr int KU = TT > 0 ? DSP_STAGE_KU : 1;
     const int r = T / 2, smax = max(r, T - 1 - r);
     double u1 = 0.0, u2 = 0.0;
     if (F.is_root) {
@@ -129,7 +133,7 @@ __device__ __forceinline__ void tw_back(const Factor &F, double &g1, double &g2,
 
 template <int TT>
 __device__ __forceinline__ void tw_solve(const Factor &F, double &g1, double &g2, int T, int lane) {
-    constexpr int KU = TT > 0 ? 16 : 1;
+    constexpr int KU = TT > 0 ? DSP_STAGE_KU : 1;
     const int r = T / 2, kmax = max(r - 1, T - 2 - r);
 #pragma unroll KU
     for (int k = 1; k <= kmax; ++k) {
@@ -316,10 +320,51 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
         make_rhs(false, g1, g2);
         PH(10);
         Sym2 Dh = D;
+        constexpr int KUF = TT > 0 ? DSP_STAGE_KU : 1;
+#ifdef DSP_DEFER_RCP
+        // deferred reciprocal: the lanes pass the eliminated block Dh itself; the receiver forms Cout adj(R) Cout' while
+        // the reciprocal of det(R) is in flight, so the dependent chain per step is  shfl -> det -> rcp -> fma
+        F.G.a = F.G.b = F.G.c = F.G.d = 0.0;
+        F.G2 = F.G;
+#pragma unroll KUF
+        for (int k = 1; k <= kmax; ++k) {
+            Sym2 R;
+            R.a = shfl_src(Dh.a, F.src); R.b = shfl_src(Dh.b, F.src); R.c = shfl_src(Dh.c, F.src);
+            const double q1 = shfl_src(g1, F.src), q2 = shfl_src(g2, F.src);
+            if (F.fo == k) {
+                const double rd = frcp(fma(R.a, R.c, -(R.b * R.b)));
+                Sym2 adj; adj.a = R.c; adj.b = -R.b; adj.c = R.a;
+                const Mat2 X = mul_ss(Cout, adj);
+                const double ya = fma(X.a, Cout.a, X.b * Cout.b), yb = fma(X.a, Cout.b, X.b * Cout.c), yc = fma(X.c, Cout.b, X.d * Cout.c);
+                const double t1 = fma(X.a, q1, X.b * q2), t2 = fma(X.c, q1, X.d * q2);
+                Dh.a = fma(-ya, rd, Dh.a); Dh.b = fma(-yb, rd, Dh.b); Dh.c = fma(-yc, rd, Dh.c);
+                g1 = fma(-t1, rd, g1); g2 = fma(-t2, rd, g2);
+                F.G.a = X.a * rd; F.G.b = X.b * rd; F.G.c = X.c * rd; F.G.d = X.d * rd;
+            }
+        }
+        {
+            Sym2 Ra, Rb;
+            const int la = max(rt - 1, 0), lb = min(rt + 1, 31);
+            Ra.a = shfl_src(Dh.a, la); Ra.b = shfl_src(Dh.b, la); Ra.c = shfl_src(Dh.c, la);
+            Rb.a = shfl_src(Dh.a, lb); Rb.b = shfl_src(Dh.b, lb); Rb.c = shfl_src(Dh.c, lb);
+            const double a1 = shfl_src(g1, la), a2 = shfl_src(g2, la), b1 = shfl_src(g1, lb), b2 = shfl_src(g2, lb);
+            if (F.is_root) {
+                if (rt >= 1) {
+                    F.G = mul_ss(Bp, inv_spd(Ra)); sub_gc(Dh, F.G, Bp);
+                    g1 -= fma(F.G.a, a1, F.G.b * a2); g2 -= fma(F.G.c, a1, F.G.d * a2);
+                }
+                if (rt + 1 <= T - 1) {
+                    F.G2 = mul_ss(Bn, inv_spd(Rb)); sub_gc(Dh, F.G2, Bn);
+                    g1 -= fma(F.G2.a, b1, F.G2.b * b2); g2 -= fma(F.G2.c, b1, F.G2.d * b2);
+                }
+            }
+        }
+        F.Dhinv = inv_spd(Dh);
+#else
         F.Dhinv = inv_spd(Dh);
         F.G.a = F.G.b = F.G.c = F.G.d = 0.0;
         F.G2 = F.G;
-#pragma unroll (TT > 0 ? 16 : 1)
+#pragma unroll KUF
         for (int k = 1; k <= kmax; ++k) {
             Sym2 R;
             R.a = shfl_src(F.Dhinv.a, F.src); R.b = shfl_src(F.Dhinv.b, F.src); R.c = shfl_src(F.Dhinv.c, F.src);
@@ -350,6 +395,7 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
                 F.Dhinv = inv_spd(Dh);
             }
         }
+#endif
         PH(11);
         // ---- affine predictor: backward sweep only
         tw_back<TT>(F, g1, g2, T, lane);

@@ -164,6 +164,33 @@ def test_host_bidder_logic(monkeypatch):
     _check_bidders(highs_lp_solve)
 
 
+def test_host_rolling_horizon_batch(monkeypatch, tmp_path):
+    """three simulations with different battery sizes advanced four tracking steps: state hand-over and the result table"""
+    monkeypatch.setattr(DLH, "_lp_solve", highs_lp_solve)
+    md = DLH.RenewableGeneratorModelData("309_WIND_1", "Carter", 0, 200)
+    m = DLH.MultiPeriodWindBattery(md, np.tile(CF, 2), 200.0, np.array([5.0, 25.0, 50.0]), np.array([20.0, 100.0, 200.0]))
+    assert m.N == 3
+    tr = DLH.Tracker(m, tracking_horizon=4, n_tracking_hour=1)
+    disp = np.array([0.5, 1.0, 10.0, 20.0])
+    for h in range(4):
+        soc_before = tr.fs.soc0.copy()
+        prof = tr.track_market_dispatch(disp, date="2020-01-02", hour=h)
+        # the SoC fixed for the next horizon is this horizon's first-hour SoC rounded to 2 decimals (double_loop.py:189-191)
+        assert np.allclose(tr.fs.soc0, np.round(prof["realized_soc"][-1], 2))
+        assert tr.fs._time_idx == h + 1 and np.allclose(tr.fs.cf[0], np.tile(CF, 2)[h + 1:h + 5])
+        first = tr.tracking_model_object.result_list[-1]
+        assert len(first) == 3 * 4 and set(first["Simulation"]) == {0, 1, 2}
+        # energy balance of the implemented hour: soc = soc0 + 0.95 in - out/0.95
+        step = tr.fs.sol["soc"][:, 0] * 0 + prof["realized_soc"][-1] - soc_before
+        assert np.all(np.abs(step) <= 0.95 * m._battery_pmax_mw * 1e3 + 1e-6)
+    m.write_results(tmp_path / "tracker.csv")
+    import pandas as pd
+    df = pd.read_csv(tmp_path / "tracker.csv")
+    assert list(df.columns[:4]) == ["Generator", "Date", "Hour", "Horizon [hr]"] and len(df) == 4 * 12
+    assert {"Total Wind Generation [MW]", "Total Power Output [MW]", "Wind Power Output [MW]", "Wind Curtailment [MW]",
+            "Battery Power Output [MW]", "Wind Power to Battery [MW]", "State of Charge [MWh]", "Total Cost [$]"} <= set(df.columns)
+
+
 def test_backcaster_order():
     bc = DLH.Backcaster({"b": np.arange(72.0)}, {"b": np.arange(72.0)})
     f = bc.forecast_day_ahead_prices("d", 0, "b", 48, 2)
