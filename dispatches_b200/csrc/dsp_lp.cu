@@ -511,12 +511,7 @@ namespace {
 #ifndef DSP_STAGE_WPB
 #define DSP_STAGE_WPB 4
 #endif
-#ifdef DSP_STAGE_MAXNREG
-__global__ void __maxnreg__(DSP_STAGE_MAXNREG) dsp_ipm_stage_wb_kernel(
-#else
-__global__ void __launch_bounds__(32 * DSP_STAGE_WPB, DSP_STAGE_MINB) dsp_ipm_stage_wb_kernel(
-#endif
-        const KParams P, const stagewb::StageParams S) {
+__global__ void __launch_bounds__(32 * DSP_STAGE_WPB, DSP_STAGE_MINB) dsp_ipm_stage_wb_kernel(const KParams P, const stagewb::StageParams S) {
     const int lane = threadIdx.x & 31;
     stagewb::Out O;
     O.obj = P.obj; O.x_out = P.x_out; O.y_out = P.y_out; O.status = P.status; O.iters = P.iters; O.n = P.n; O.m = P.m;
@@ -536,11 +531,7 @@ __global__ void __launch_bounds__(32 * DSP_STAGE_WPB, DSP_STAGE_MINB) dsp_ipm_st
         int it0 = 0;
         for (int attempt = 0; attempt < 2; ++attempt) {
             const double sf = attempt ? 0.99 : P.step_frac, rg = attempt ? 10.0 * P.reg : P.reg;
-            int r;
-            if (S.T == 24)
-                r = stagewb::solve_one<24>(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, sf, rg, P.max_iter, O, lane, it0);
-            else
-                r = stagewb::solve_one<0>(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, sf, rg, P.max_iter, O, lane, it0);
+            const int r = stagewb::solve_one(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, sf, rg, P.max_iter, O, lane, it0);
             if (r == 0) break;
             it0 = r - 1;
         }

@@ -70,10 +70,6 @@ __device__ __forceinline__ double wsum(double v) {
     return v;
 }
 
-#ifndef DSP_STAGE_KU
-#define DSP_STAGE_KU 16
-#endif
-
 struct Sym2 { double a, b, c; };            // [[a, b], [b, c]]
 struct Mat2 { double a, b, c, d; };         // [[a, b], [c, d]]
 
@@ -109,16 +105,14 @@ struct Factor {          // per-lane pieces of the twisted block LDL'
 };
 
 // backward half of the solve: on entry (g1, g2) is the forward-eliminated right-hand side, on exit the solution
-template <int TT>
 __device__ __forceinline__ void tw_back(const Factor &F, double &g1, double &g2, int T, int lane) {
-    constexpr int KU = TT > 0 ? DSP_STAGE_KU : 1;
     const int r = T / 2, smax = max(r, T - 1 - r);
     double u1 = 0.0, u2 = 0.0;
     if (F.is_root) {
         u1 = fma(F.Dhinv.a, g1, F.Dhinv.b * g2);
         u2 = fma(F.Dhinv.b, g1, F.Dhinv.c * g2);
     }
-#pragma unroll KU
+#pragma unroll 1
     for (int s = 1; s <= smax; ++s) {
         const double r1 = shfl_src(u1, F.bsrc), r2 = shfl_src(u2, F.bsrc);
         if (F.bo == s) {
@@ -131,11 +125,9 @@ __device__ __forceinline__ void tw_back(const Factor &F, double &g1, double &g2,
     g1 = u1; g2 = u2;
 }
 
-template <int TT>
 __device__ __forceinline__ void tw_solve(const Factor &F, double &g1, double &g2, int T, int lane) {
-    constexpr int KU = TT > 0 ? DSP_STAGE_KU : 1;
     const int r = T / 2, kmax = max(r - 1, T - 2 - r);
-#pragma unroll KU
+#pragma unroll 1
     for (int k = 1; k <= kmax; ++k) {
         const double r1 = shfl_src(g1, F.src), r2 = shfl_src(g2, F.src);
         if (F.fo == k) {
@@ -151,7 +143,7 @@ __device__ __forceinline__ void tw_solve(const Factor &F, double &g1, double &g2
             if (r + 1 <= T - 1) { g1 -= fma(F.G2.a, b1, F.G2.b * b2); g2 -= fma(F.G2.c, b1, F.G2.d * b2); }
         }
     }
-    tw_back<TT>(F, g1, g2, T, lane);
+    tw_back(F, g1, g2, T, lane);
 }
 
 struct Out {
@@ -160,11 +152,12 @@ struct Out {
     int n, m;
 };
 
-// solves LP number p; all 32 lanes of the warp participate.  TT > 0: horizon known at compile time (loops unroll)
-template <int TT>
+// solves LP number p; all 32 lanes of the warp participate.  The sweep loops are deliberately NOT unrolled and the horizon
+// is a run-time value: the iteration body is ~3k instructions, and a T=24 instantiation with unrolled sweeps (7k) ran 5 %
+// slower -- instruction-cache misses were 18 % of the stall samples (profiles/stage_variants_r1.log)
 __device__ int solve_one(const StageParams &S, const double *cp, const double *rpar, double kconst, long long p,
                           double tol, double feas_tol, double step_frac, double reg, int max_iter, const Out &O, int lane, int it0) {
-    const int T = TT > 0 ? TT : S.T;
+    const int T = S.T;
     const bool act = lane < T, has_s = lane < T - 1;
     const double a = S.a, binv = S.binv, hf = S.hf, dl = S.dl;
     // ---- problem data of this period
@@ -320,13 +313,11 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
         make_rhs(false, g1, g2);
         PH(10);
         Sym2 Dh = D;
-        constexpr int KUF = TT > 0 ? DSP_STAGE_KU : 1;
-#ifdef DSP_DEFER_RCP
         // deferred reciprocal: the lanes pass the eliminated block Dh itself; the receiver forms Cout adj(R) Cout' while
         // the reciprocal of det(R) is in flight, so the dependent chain per step is  shfl -> det -> rcp -> fma
         F.G.a = F.G.b = F.G.c = F.G.d = 0.0;
         F.G2 = F.G;
-#pragma unroll KUF
+#pragma unroll 1
         for (int k = 1; k <= kmax; ++k) {
             Sym2 R;
             R.a = shfl_src(Dh.a, F.src); R.b = shfl_src(Dh.b, F.src); R.c = shfl_src(Dh.c, F.src);
@@ -360,45 +351,9 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
             }
         }
         F.Dhinv = inv_spd(Dh);
-#else
-        F.Dhinv = inv_spd(Dh);
-        F.G.a = F.G.b = F.G.c = F.G.d = 0.0;
-        F.G2 = F.G;
-#pragma unroll KUF
-        for (int k = 1; k <= kmax; ++k) {
-            Sym2 R;
-            R.a = shfl_src(F.Dhinv.a, F.src); R.b = shfl_src(F.Dhinv.b, F.src); R.c = shfl_src(F.Dhinv.c, F.src);
-            const double q1 = shfl_src(g1, F.src), q2 = shfl_src(g2, F.src);
-            if (F.fo == k) {
-                F.G = mul_ss(Cout, R);
-                g1 -= fma(F.G.a, q1, F.G.b * q2);
-                g2 -= fma(F.G.c, q1, F.G.d * q2);
-                sub_gc(Dh, F.G, Cout);
-                F.Dhinv = inv_spd(Dh);
-            }
-        }
-        {
-            Sym2 Ra, Rb;
-            const int la = max(rt - 1, 0), lb = min(rt + 1, 31);
-            Ra.a = shfl_src(F.Dhinv.a, la); Ra.b = shfl_src(F.Dhinv.b, la); Ra.c = shfl_src(F.Dhinv.c, la);
-            Rb.a = shfl_src(F.Dhinv.a, lb); Rb.b = shfl_src(F.Dhinv.b, lb); Rb.c = shfl_src(F.Dhinv.c, lb);
-            const double a1 = shfl_src(g1, la), a2 = shfl_src(g2, la), b1 = shfl_src(g1, lb), b2 = shfl_src(g2, lb);
-            if (F.is_root) {
-                if (rt >= 1) {
-                    F.G = mul_ss(Bp, Ra); sub_gc(Dh, F.G, Bp);
-                    g1 -= fma(F.G.a, a1, F.G.b * a2); g2 -= fma(F.G.c, a1, F.G.d * a2);
-                }
-                if (rt + 1 <= T - 1) {
-                    F.G2 = mul_ss(Bn, Rb); sub_gc(Dh, F.G2, Bn);
-                    g1 -= fma(F.G2.a, b1, F.G2.b * b2); g2 -= fma(F.G2.c, b1, F.G2.d * b2);
-                }
-                F.Dhinv = inv_spd(Dh);
-            }
-        }
-#endif
         PH(11);
         // ---- affine predictor: backward sweep only
-        tw_back<TT>(F, g1, g2, T, lane);
+        tw_back(F, g1, g2, T, lane);
         PH(12);
         recover(g1, g2);
         // dz = ax/x - z - z dx / x ;  dw = as/s - w - w ds / s
@@ -430,7 +385,7 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
         PH(13);
         // ---- corrector
         make_rhs(true, g1, g2);
-        tw_solve<TT>(F, g1, g2, T, lane);
+        tw_solve(F, g1, g2, T, lane);
         PH(14);
         recover(g1, g2);
         dzg = (smu - cg) * rxg - zg - zg * dxg * rxg; dzi = (smu - ci) * rxi - zi - zi * dxi * rxi;

@@ -3,14 +3,13 @@ import subprocess, sys, concurrent.futures as cf
 sys.path.insert(0, ".")
 from dispatches_b200.csrc import build as B
 VARIANTS = {
-    "v0_base": [],
-    "v1_defer": ["-DDSP_DEFER_RCP"],
-    "v2_base_r144": ["-DDSP_STAGE_WPB=2", "-DDSP_STAGE_MAXNREG=144"],
-    "v3_defer_r144": ["-DDSP_DEFER_RCP", "-DDSP_STAGE_WPB=2", "-DDSP_STAGE_MAXNREG=144"],
-    "v7_defer_r152": ["-DDSP_DEFER_RCP", "-DDSP_STAGE_WPB=1", "-DDSP_STAGE_MAXNREG=152"],
-    "v4_base_ku4": ["-DDSP_STAGE_KU=4"],
-    "v5_defer_ku4": ["-DDSP_DEFER_RCP", "-DDSP_STAGE_KU=4"],
-    "v6_defer_ku1": ["-DDSP_DEFER_RCP", "-DDSP_STAGE_KU=1"],
+    "a0_base_ku16": [],
+    "a1_base_ku1": ["-DDSP_STAGE_KU=1"],
+    "a2_base_ku2": ["-DDSP_STAGE_KU=2"],
+    "a3_defer_ku1": ["-DDSP_DEFER_RCP", "-DDSP_STAGE_KU=1"],
+    "a4_defer_ku2": ["-DDSP_DEFER_RCP", "-DDSP_STAGE_KU=2"],
+    "a5_generic_base": ["-DDSP_STAGE_GENERIC_ONLY"],
+    "a6_generic_defer": ["-DDSP_STAGE_GENERIC_ONLY", "-DDSP_DEFER_RCP"],
 }
 out = B.ROOT / "build" / "variants"
 out.mkdir(parents=True, exist_ok=True)
