@@ -25,11 +25,14 @@ from .solver import BatchLPSolver, OPTIMAL
 _SOLVERS = {}
 
 
-def _lp_solve(mode, T, cparams, rparams, n_tracking_hour=1, options=None):
+_FAMILIES = {"wind_battery": TP.wind_battery_operation, "nuclear": TP.nuclear_operation}
+
+
+def _lp_solve(mode, T, cparams, rparams, n_tracking_hour=1, options=None, family="wind_battery"):
     """One batched solve of the operation template; returns (obj [N], status [N], columns {name: [N,T]})."""
-    key = (mode, T, n_tracking_hour, tuple(sorted((options or {}).items())))
+    key = (family, mode, T, n_tracking_hour, tuple(sorted((options or {}).items())))
     if key not in _SOLVERS:
-        _SOLVERS[key] = BatchLPSolver(TP.wind_battery_operation(T, mode, n_tracking_hour), **(options or {}))
+        _SOLVERS[key] = BatchLPSolver(_FAMILIES[family](T, mode, n_tracking_hour), **(options or {}))
     sol = _SOLVERS[key]
     r = sol.solve_host(np.ascontiguousarray(cparams), np.ascontiguousarray(rparams), want_x=True)
     return r.obj, r.status, _columns(sol.t, sol.to_model_space(r.x), T)
@@ -39,7 +42,9 @@ _COLS = dict(grid="blk[{t}].fs.splitter.grid_elec[0]", batt_in="blk[{t}].fs.batt
              batt_out="blk[{t}].fs.battery.elec_out[0]", soc="blk[{t}].fs.battery.state_of_charge[0]",
              throughput="blk[{t}].fs.battery.energy_throughput[0]", waste="wind_waste_kw[{t}]",
              under="power_underdelivered_kw[{t}]", over="power_overdelivered_kw[{t}]",
-             da="day_ahead_power_kw[{t}]", underbid="real_time_underbid_power_kw[{t}]")
+             da="day_ahead_power_kw[{t}]", underbid="real_time_underbid_power_kw[{t}]",
+             pem="blk[{t}].fs.pem.electricity[0]", pipeline="blk[{t}].fs.h2_tank.outlet_to_pipeline.flow_mol[0]",
+             holdup="blk[{t}].fs.h2_tank.tank_holdup[0]")
 
 
 def _columns(template, xm, T):
@@ -180,6 +185,14 @@ class MultiPeriodWindBattery:
         return TP.wind_battery_operation_rparams(b.horizon, b.cf, self._wind_pmax_mw, self._battery_pmax_mw,
                                                  self._battery_energy_capacity_mwh, b.soc0, b.thr0, signal_mw)
 
+    def _lp(self, b, mode, da=None, rt=None, signal_mw=None, n_tracking_hour=1, options=None):
+        """Solves the block's LP in the given mode for all N simulations and loads the solution into the block."""
+        pen = np.full((self.N, 1), b.wind_waste_penalty)
+        cp = pen if mode == "tracker" else np.concatenate([da, rt, pen], axis=1)
+        obj, status, cols = _lp_solve(mode, b.horizon, cp, self._rparams(b, signal_mw), n_tracking_hour, options, "wind_battery")
+        self._load_solution(b, cols)
+        return obj, status, cols
+
     def _load_solution(self, b, cols):
         b.sol = cols
         b.P_T = (cols["grid"] + cols["batt_out"]) * 1e-3                                                      # :168
@@ -234,6 +247,84 @@ class MultiPeriodWindBattery:
         return ("tot_cost", 1)
 
 
+class MultiPeriodNuclear:
+    """nuclear_flowsheet_multiperiod_class.py:158-344 (500 MW NPP + 100 MW PEM + 5000 kg tank, :97-102).  ``n_sim``
+    independent simulations share the plant data and differ in their market signals / implemented hold-ups."""
+    MW_H2 = 2.016e-3
+
+    def __init__(self, model_data, n_sim=1, h2_price=4.0):
+        self.model_data = model_data
+        self.p_lower, self.p_upper, self.generator = model_data.p_min, model_data.p_max, model_data.gen_name   # :181-183
+        self.N, self.h2_price = int(n_sim), h2_price
+        self.result_list = []
+
+    def populate_model(self, blk, horizon):
+        blk.horizon = horizon
+        blk.holdup0 = np.zeros(self.N)                              # tank_holdup_previous of block 0 fixed to 0 (:203)
+        return blk
+
+    def update_model(self, b, implemented_tank_holdup):
+        b.holdup0 = np.round(np.broadcast_to(np.asarray(implemented_tank_holdup[-1], float), (self.N,)))   # :232-235
+
+    def _lp(self, b, mode, da=None, rt=None, signal_mw=None, n_tracking_hour=1, options=None):
+        T = b.horizon
+        h2 = np.full((self.N, 1), self.h2_price)
+        cp = h2 if mode == "tracker" else np.concatenate([da, rt, h2], axis=1)
+        sig = np.zeros((self.N, T)) if signal_mw is None else np.broadcast_to(np.atleast_2d(np.asarray(signal_mw, float)), (self.N, T))
+        rp = np.concatenate([b.holdup0[:, None], sig], axis=1)
+        obj, status, cols = _lp_solve(mode, T, cp, rp, n_tracking_hour, options, "nuclear")
+        E = TP.NUC_NP_CAPACITY_MW * 1e3
+        b.sol = cols
+        b.P_T = (E - cols["pem"]) * 1e-3                                                             # :211
+        b.tot_cost = (E * 1e-3 * 2.3 + cols["pem"] * 1e-3 * 1.3 + cols["holdup"] * self.MW_H2 * 0.01
+                      - cols["pipeline"] * self.MW_H2 * 3600.0 * self.h2_price)                      # :149-153, :212
+        return obj, status, cols
+
+    @staticmethod
+    def get_last_delivered_power(b, last_implemented_time_step):
+        return b.P_T[:, last_implemented_time_step]                                                  # :252
+
+    @staticmethod
+    def get_implemented_profile(b, last_implemented_time_step):
+        return {"implemented_tank_holdup": deque(b.sol["holdup"][:, t] for t in range(last_implemented_time_step + 1))}
+
+    def record_results(self, blk, date=None, hour=None, **kwargs):
+        """Rows of the reference's table (:281-320)."""
+        import pandas as pd
+        prev = np.concatenate([blk.holdup0[:, None], blk.sol["holdup"][:, :-1]], axis=1)
+        rows = []
+        for k in range(self.N):
+            for t in range(blk.horizon):
+                row = {"Date": date, "Hour": hour, "Horizon [hr]": int(t),
+                       "Power to Grid [MW]": round(float(blk.P_T[k, t]), 2),
+                       "Power to PEM [MW]": round(float(blk.sol["pem"][k, t] * 1e-3), 2),
+                       "Initial holdup [kg]": round(float(prev[k, t] * self.MW_H2), 2),
+                       "Final holdup [kg]": round(float(blk.sol["holdup"][k, t] * self.MW_H2), 2),
+                       "Hydrogen Market [kg/hr]": round(float(blk.sol["pipeline"][k, t] * self.MW_H2 * 3600), 2),
+                       "Total Cost [$]": round(float(blk.tot_cost[k, t]), 2)}
+                if self.N > 1:
+                    row["Simulation"] = k
+                row.update(kwargs)
+                rows.append(row)
+        self.result_list.append(pd.DataFrame(rows))
+
+    def write_results(self, path):
+        import pandas as pd
+        pd.concat(self.result_list).to_csv(path, index=False)
+
+    @property
+    def power_output(self):
+        return "P_T"
+
+    @property
+    def total_cost(self):
+        return ("tot_cost", 1)
+
+    @property
+    def pmin(self):
+        return self.p_lower
+
+
 class Tracker:
     """idaes Tracker as the reference drives it (test_multiperiod_wind_battery_doubleloop.py:68-87): one LP per call of
     ``track_market_dispatch`` over ``tracking_horizon`` hours, the first ``n_tracking_hour`` tracked hard."""
@@ -255,12 +346,11 @@ class Tracker:
         obj_ = self.tracking_model_object
         N, H = obj_.N, self.tracking_horizon
         md = np.broadcast_to(np.atleast_2d(np.asarray(market_dispatch, float)), (N, H))
-        obj, status, cols = _lp_solve("tracker", H, np.full((N, 1), self.fs.wind_waste_penalty), obj_._rparams(self.fs, md),
-                                      self.n_tracking_hour, self.solver_options)
+        obj, status, cols = obj_._lp(self.fs, "tracker", signal_mw=md, n_tracking_hour=self.n_tracking_hour,
+                                     options=self.solver_options)
         self.status = status
         if np.any(status != OPTIMAL):
             raise RuntimeError(f"tracking LP not optimal for simulations {np.nonzero(status != OPTIMAL)[0][:8].tolist()}")
-        obj_._load_solution(self.fs, cols)
         self.objective = obj
         self.power_underdelivered, self.power_overdelivered = cols["under"] * 1e-3, cols["over"] * 1e-3
         obj_.record_results(self.fs, date=date, hour=hour)
@@ -299,11 +389,9 @@ class _StochasticProgramBidder:
     def _solve(self, blk, mode, da, rt, da_dispatch=None):
         obj_ = self.bidding_model_object
         N, H = obj_.N, blk.horizon
-        cp = np.concatenate([da, rt, np.full((N, 1), blk.wind_waste_penalty)], axis=1)
-        obj, status, cols = _lp_solve(mode, H, cp, obj_._rparams(blk, da_dispatch), 1, self.solver_options)
+        obj, status, cols = obj_._lp(blk, mode, da=da, rt=rt, signal_mw=da_dispatch, options=self.solver_options)
         if np.any(status != OPTIMAL):
             raise RuntimeError(f"bidding LP not optimal for simulations {np.nonzero(status != OPTIMAL)[0][:8].tolist()}")
-        obj_._load_solution(blk, cols)
         if da_dispatch is not None:                      # constant dropped from the template (bilinear in the parameters)
             obj = obj - np.sum((da - rt) * da_dispatch, axis=1)
         blk.objective = -obj                             # the IDAES objective is a maximisation

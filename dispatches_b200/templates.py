@@ -369,3 +369,50 @@ def wind_battery_operation_rparams(T, cf, wind_mw, batt_mw, energy_mwh, soc0_kwh
     sig = np.zeros((N, T)) if signal_mw is None else np.broadcast_to(np.atleast_2d(np.asarray(signal_mw, float)), (N, T))
     return np.ascontiguousarray(np.concatenate(
         [cf * W, col(batt_mw, 1e3), col(energy_mwh, 1e3), col(soc0_kwh), col(thr0_kwh), W, sig], axis=1))
+
+
+NUC_NP_CAPACITY_MW = 500.0       # flowsheet_options of create_multiperiod_nuclear_model (…_class.py:97-102)
+
+
+def nuclear_operation(T: int, mode: str, n_tracking_hour: int = 1, np_capacity=NUC_NP_CAPACITY_MW, pem_capacity=100.0,
+                      tank_capacity=5000.0, h2_demand=0.35) -> LPTemplate:
+    """MultiPeriodNuclear's operation model (nuclear_flowsheet_multiperiod_class.py:72-155, :190-215) under the Tracker /
+    Bidder objectives (see wind_battery_operation).  P_T = np_to_grid * 1e-3 = (E - pem.electricity) * 1e-3.
+    rparams = [tank_holdup_previous of block 0 (mol), dispatch_or_da_dispatch_MW_t (T)]
+    cparams = tracker: [h2_price];  bidder_*: [da_t (T), rt_t (T), h2_price]"""
+    assert mode in ("tracker", "bidder_da", "bidder_rt")
+    E = np_capacity * 1e3
+    Pc = 1 if mode == "tracker" else 2 * T + 1
+    iH2, iH0, iD = Pc - 1, 0, 1
+    B = TemplateBuilder(f"nuclear_{mode}_T{T}", Pc=Pc, Pr=T + 1)
+    xp, u, H = {}, {}, {}
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        xp[t] = B.var(p + "pem.electricity[0]", ub=pem_capacity * 1e3)
+        u[t] = B.var(p + "h2_tank.outlet_to_pipeline.flow_mol[0]", ub=h2_demand / MW_H2)
+        H[t] = B.var(p + "h2_tank.tank_holdup[0]", ub=(tank_capacity / MW_H2 if t < T - 1 else None))
+        B.cost(xp[t], 1e-3 * 1.3); B.cost(H[t], MW_H2 * 0.01)                # operating_cost :149-153
+        B.cost(u[t], (0.0, {iH2: -MW_H2 * 3600.0}))
+        B.obj_const(E * 1e-3 * 2.3)
+    for t in range(T):
+        row = {H[t]: 1.0, xp[t]: -3600.0 * NUC_PEM_ELEC_TO_MOL, u[t]: 3600.0}
+        if t > 0:
+            row[H[t - 1]] = -1.0
+        B.eq(f"tank_balance[{t}]", row, (0.0, {iH0: 1.0}) if t == 0 else 0.0)  # :203, :233-235
+        if mode == "tracker":
+            un = B.var(f"power_underdelivered_kw[{t}]"); ov = B.var(f"power_overdelivered_kw[{t}]")
+            pen = LARGE_PENALTY if t < n_tracking_hour else LARGE_PENALTY / max(1, T - n_tracking_hour)
+            B.cost(un, pen * 1e-3); B.cost(ov, pen * 1e-3)
+            B.eq(f"tracking_dispatch[{t}]", {xp[t]: -1.0, un: 1.0, ov: -1.0}, (-E, {iD + t: 1e3}))
+        else:
+            B.cost(xp[t], (0.0, {T + t: 1e-3})); B.ocmap[T + t] += -1e-3 * E   # -rt * (E - xp) * 1e-3
+            if mode == "bidder_da":
+                da = B.var(f"day_ahead_power_kw[{t}]")
+                B.cost(da, (0.0, {t: -1e-3, T + t: 1e-3}))
+                B.le(f"day_ahead_power_ub[{t}]", {da: 1.0, xp[t]: 1.0}, E)
+            else:
+                ub = B.var(f"real_time_underbid_power_kw[{t}]"); sp_ = B.var(f"surplus_kw[{t}]")
+                B.cost(ub, LARGE_PENALTY * 1e-3)
+                B.eq(f"day_ahead_power_ub[{t}]", {xp[t]: -1.0, ub: 1.0, sp_: -1.0}, (-E, {iD + t: 1e3}))
+    B.meta.update(kind="nuclear_operation", mode=mode, T=T, E=E, n_tracking_hour=n_tracking_hour)
+    return B.build(equilibrate=True)

@@ -28,7 +28,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .lp_models import (_Builder, BATT_CAP_COST_KW, DEGRADATION, ETA_C, ETA_D, WIND_OP_COST)
+from .lp_models import (_Builder, BATT_CAP_COST_KW, DEGRADATION, ETA_C, ETA_D, WIND_OP_COST, nuclear_blocks, nuclear_operating_cost)
 
 BATT_REP_COST_KWH = BATT_CAP_COST_KW * 0.5 / 4.0     # load_parameters.py:48
 WASTE_PENALTY = 1e3                                  # wind_battery_double_loop.py:165
@@ -110,6 +110,56 @@ def bidder_raw(da, rt, cf, wind_mw=200.0, batt_mw=25.0, energy_mwh=100.0, soc0=0
             B.cost(j, a)
         B.c0 += cost[t][1]
     return B.finish(dict(kind="bidder", T=H, v=v))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# nuclear + PEM + tank: MultiPeriodNuclear (case_studies/nuclear_case/nuclear_flowsheet_multiperiod_class.py:158-344)
+#   :190-215 populate_model  (holdup_previous of block 0 fixed; P_T = np_to_grid * 1e-3; tot_cost = operating_cost)
+#   :218-237 update_model    (implemented holdup rounded to an integer and fixed)
+# No known answers exist in the reference for these LPs (nuclear_case/tests has no double-loop test): unpinned beyond
+# the rows / constants shared with the price-taker LP.
+# ---------------------------------------------------------------------------------------------------------------
+def _nuclear_forms(B, v, T, holdup0, h2_price, **kw):
+    nuclear_blocks(B, v, T, holdup0=holdup0, **kw)
+    PT = [({v["xg", t]: 1e-3}, 0.0) for t in range(T)]
+    cost = [(nuclear_operating_cost(v, t, h2_price), 0.0) for t in range(T)]
+    return PT, cost
+
+
+def nuclear_tracker_raw(dispatch, holdup0=0.0, h2_price=4.0, n_tracking_hour=1, **kw):
+    dispatch = np.asarray(dispatch, float); H = dispatch.size
+    B = _Builder(); v = {}
+    PT, cost = _nuclear_forms(B, v, H, holdup0, h2_price, **kw)
+    for t in range(H):
+        v["under", t] = B.var(f"power_underdelivered[{t}]")
+        v["over", t] = B.var(f"power_overdelivered[{t}]")
+        row = dict(PT[t][0]); row[v["under", t]] = 1.0; row[v["over", t]] = -1.0
+        B.eq(row, dispatch[t])
+        pen = LARGE_PENALTY if t < n_tracking_hour else LARGE_PENALTY / max(1, H - n_tracking_hour)
+        B.cost(v["under", t], pen); B.cost(v["over", t], pen)
+        for j, a in cost[t][0].items():
+            B.cost(j, a)
+    return B.finish(dict(kind="nuclear_tracker", T=H, v=v))
+
+
+def nuclear_bidder_raw(da, rt, holdup0=0.0, h2_price=4.0, da_dispatch=None, **kw):
+    da = np.asarray(da, float); rt = np.asarray(rt, float); H = da.size
+    B = _Builder(); v = {}
+    PT, cost = _nuclear_forms(B, v, H, holdup0, h2_price, **kw)
+    for t in range(H):
+        v["da", t] = B.var(f"day_ahead_power[{t}]", fix=None if da_dispatch is None else float(da_dispatch[t]))
+        v["ub", t] = B.var(f"real_time_underbid_power[{t}]", fix=0.0 if da_dispatch is None else None)
+        row = {v["da", t]: 1.0, v["ub", t]: -1.0}
+        for j, a in PT[t][0].items():
+            row[j] = row.get(j, 0.0) - a
+        B.le(row, 0.0)
+        B.cost(v["da", t], -(da[t] - rt[t]))
+        for j, a in PT[t][0].items():
+            B.cost(j, -rt[t] * a)
+        B.cost(v["ub", t], LARGE_PENALTY)
+        for j, a in cost[t][0].items():
+            B.cost(j, a)
+    return B.finish(dict(kind="nuclear_bidder", T=H, v=v))
 
 
 def backcast(historical, hour, horizon, n_samples):

@@ -287,6 +287,17 @@ def nuclear_raw(lmp, np_capacity=500.0, pem_capacity=100.0, tank_capacity=5000.0
     """
     lmp = np.asarray(lmp, float); T = lmp.size
     B = _Builder(); v = {}
+    nuclear_blocks(B, v, T, np_capacity, pem_capacity, tank_capacity, h2_demand)
+    for t in range(T):
+        # objective (minimise cost - revenue)
+        B.cost_lmp(v["xg", t], t, -1e-3, lmp)
+        for j, a in nuclear_operating_cost(v, t, h2_price).items():
+            B.cost(j, a)
+    return B.finish(dict(kind="nuclear", T=T, v=v))
+
+
+def nuclear_blocks(B, v, T, np_capacity=500.0, pem_capacity=100.0, tank_capacity=5000.0, h2_demand=0.35, holdup0=0.0):
+    """The T period blocks + holdup links of create_multiperiod_nuclear_model (rows only, no objective)."""
     E = np_capacity * 1e3
     for t in range(T):
         p = f"blk[{t}].fs."
@@ -310,16 +321,14 @@ def nuclear_raw(lmp, np_capacity=500.0, pem_capacity=100.0, tank_capacity=5000.0
         B.eq({v["f", t]: 1.0, v["fi", t]: -1.0})                              # arc pem -> tank
         B.eq({v["H", t]: 1.0, v["Hp", t]: -1.0, v["fi", t]: -3600.0,
               v["u", t]: 3600.0, v["vt", t]: 3600.0})
-        # objective (minimise cost - revenue)
-        B.cost_lmp(v["xg", t], t, -1e-3, lmp)
-        B.cost(v["E", t], 1e-3 * 2.3)
-        B.cost(v["xp", t], 1e-3 * 1.3)
-        B.cost(v["H", t], MW_H2 * 0.01)
-        B.cost(v["u", t], -MW_H2 * 3600.0 * h2_price)
     for t in range(T - 1):
         B.eq({v["H", t]: 1.0, v["Hp", t + 1]: -1.0})
-    B.lb[v["Hp", 0]] = B.ub[v["Hp", 0]] = 0.0
-    return B.finish(dict(kind="nuclear", T=T, v=v))
+    B.lb[v["Hp", 0]] = B.ub[v["Hp", 0]] = float(holdup0)
+
+
+def nuclear_operating_cost(v, t, h2_price=4.0):
+    """fs.operating_cost of period t as a linear form (nuclear_flowsheet_multiperiod_class.py:149-153)."""
+    return {v["E", t]: 1e-3 * 2.3, v["xp", t]: 1e-3 * 1.3, v["H", t]: MW_H2 * 0.01, v["u", t]: -MW_H2 * 3600.0 * h2_price}
 
 
 # --------------------------------------------------------------------------------------

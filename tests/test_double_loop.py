@@ -30,9 +30,9 @@ def solve_template(t, cp, rp):
     return r.fun + k, r.x
 
 
-def highs_lp_solve(mode, T, cparams, rparams, n_tracking_hour=1, options=None):
+def highs_lp_solve(mode, T, cparams, rparams, n_tracking_hour=1, options=None, family="wind_battery"):
     """Stand-in for dispatches_b200.double_loop._lp_solve on a box without a GPU (tests only)."""
-    t = TP.wind_battery_operation(T, mode, n_tracking_hour)
+    t = DLH._FAMILIES[family](T, mode, n_tracking_hour)
     objs, xs = zip(*(solve_template(t, cp, rp) for cp, rp in zip(cparams, rparams)))
     xm = np.array(xs) * t.col_scale + t.col_shift
     return np.array(objs), np.zeros(len(objs), np.int32), DLH._columns(t, xm, T)
@@ -191,6 +191,58 @@ def test_host_rolling_horizon_batch(monkeypatch, tmp_path):
             "Battery Power Output [MW]", "Wind Power to Battery [MW]", "State of Charge [MWh]", "Total Cost [$]"} <= set(df.columns)
 
 
+@pytest.mark.parametrize("T", [4, 48])
+def test_nuclear_operation_templates_match_raw_oracle(T):
+    rng = np.random.default_rng(T)
+    da = rng.uniform(5, 60, T); rt = da + rng.normal(0, 8, T); h0 = 812345.0; disp = rng.uniform(380, 520, T)
+    rp = np.r_[h0, disp]
+    a, _ = solve_template(TP.nuclear_operation(T, "tracker"), np.array([4.0]), rp)
+    b, _ = H.solve(DL.nuclear_tracker_raw(disp, h0))
+    assert a == pytest.approx(b, rel=1e-10, abs=1e-7)
+    a, _ = solve_template(TP.nuclear_operation(T, "bidder_da"), np.r_[da, rt, 4.0], rp)
+    b, _ = H.solve(DL.nuclear_bidder_raw(da, rt, h0))
+    assert a == pytest.approx(b, rel=1e-10, abs=1e-7)
+    a, _ = solve_template(TP.nuclear_operation(T, "bidder_rt"), np.r_[da, rt, 4.0], rp)
+    b, _ = H.solve(DL.nuclear_bidder_raw(da, rt, h0, da_dispatch=disp))
+    assert a - float(np.sum((da - rt) * disp)) == pytest.approx(b, rel=1e-10, abs=1e-6)
+
+
+def _check_nuclear(n_sim):
+    """MultiPeriodNuclear under the Tracker and the SelfScheduler: objectives against the raw oracle, state hand-over."""
+    rng = np.random.default_rng(5)
+    md = DLH.ThermalGeneratorModelData(gen_name="121_NUCLEAR_1", bus="Attlee", p_min=400, p_max=500)
+    m = DLH.MultiPeriodNuclear(md, n_sim=n_sim)
+    tr = DLH.Tracker(m, tracking_horizon=4, n_tracking_hour=1)
+    holdup = np.zeros(n_sim)
+    for h in range(3):
+        disp = rng.uniform(400, 500, (n_sim, 4))
+        prof = tr.track_market_dispatch(disp, date="2020-07-10", hour=h)
+        for k in range(min(n_sim, 4)):
+            ref, _ = H.solve(DL.nuclear_tracker_raw(disp[k], holdup[k]))
+            assert tr.objective[k] == pytest.approx(ref, rel=1e-7, abs=1e-5)
+        assert np.allclose(tr.power_output[:, 0], disp[:, 0], atol=1e-3)                  # hard-tracked hour
+        holdup = np.round(prof["implemented_tank_holdup"][-1])
+        assert np.array_equal(tr.fs.holdup0, holdup)                                       # :232-235 integer rounding
+    bc = DLH.Backcaster({"Attlee": rng.uniform(5, 60, 48)}, {"Attlee": rng.uniform(5, 60, 48)})
+    ss = DLH.SelfScheduler(DLH.MultiPeriodNuclear(md, n_sim=n_sim), day_ahead_horizon=48, real_time_horizon=4, n_scenario=1, forecaster=bc)
+    bids = ss.compute_day_ahead_bids(date="2020-07-10")
+    da = bc.forecast_day_ahead_prices("d", 0, "Attlee", 48, 1)[0]; rt = bc.forecast_real_time_prices("d", 0, "Attlee", 48, 1)[0]
+    ref, _ = H.solve(DL.nuclear_bidder_raw(da, rt, 0.0))
+    assert -ss.day_ahead_model.objective[0] == pytest.approx(ref, rel=1e-8)
+    pmax = np.array([np.atleast_1d(b["121_NUCLEAR_1"]["p_max"])[0] for b in bids.values()])
+    # day-ahead quantity: all of P_T where da > rt, nothing where da < rt; P_T in [400, 500] (NPP 500 MW, PEM <= 100 MW)
+    assert np.all((pmax < 1e-3) | ((pmax >= 400 - 1e-3) & (pmax <= 500 + 1e-3)))
+    assert np.all(pmax[da > rt + 1e-9] >= 400 - 1e-3) and np.all(pmax[da < rt - 1e-9] < 1e-3)
+    df = ss.bidding_model_object.result_list[0]
+    assert {"Power to Grid [MW]", "Power to PEM [MW]", "Initial holdup [kg]", "Final holdup [kg]", "Hydrogen Market [kg/hr]",
+            "Total Cost [$]"} <= set(df.columns)
+
+
+def test_host_nuclear_logic(monkeypatch):
+    monkeypatch.setattr(DLH, "_lp_solve", highs_lp_solve)
+    _check_nuclear(2)
+
+
 def test_backcaster_order():
     bc = DLH.Backcaster({"b": np.arange(72.0)}, {"b": np.arange(72.0)})
     f = bc.forecast_day_ahead_prices("d", 0, "b", 48, 2)
@@ -209,6 +261,11 @@ def test_gpu_tracker_known_answer():
 @pytest.mark.gpu
 def test_gpu_bidders_known_answers():
     _check_bidders(None)
+
+
+@pytest.mark.gpu
+def test_gpu_nuclear_double_loop():
+    _check_nuclear(64)
 
 
 @pytest.mark.gpu
