@@ -249,11 +249,11 @@ def main():
         fp64_peak = None
     # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), not measured live
     traffic = None
-    for f in sorted((ROOT / "profiles").glob("prof_r*_stage*.summary.json")):
-        try:
-            traffic = float(json.load(open(f))["traffic_bytes_per_launch"])
-        except Exception:
-            pass
+    try:
+        cur = json.load(open(ROOT / "profiles" / "current.json"))["stage_profile"]
+        traffic = float(json.load(open(ROOT / "profiles" / cur))["traffic_bytes_per_launch"])
+    except Exception:
+        pass
     line = {"metric": METRIC, "value": value, "unit": "LPs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config(world),

@@ -886,6 +886,10 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         ws_mode = true;
         warps = 2;
     }
+    if (const char *e = getenv("DSP_BAND_WS_WARPS")) {        // experiment switch: force the global-workspace mode
+        const long long f = atoll(e);
+        if (f > 0) { ws_mode = true; warps = f; hot_in_smem = 0; off = 16; }
+    }
     warps = std::min<long long>(warps, kMaxWarps);
     long long ctas = std::min<long long>(T->sm_count, (N + warps - 1) / warps);
     // spread a small batch over all SMs
