@@ -372,3 +372,21 @@ def test_long_horizon_wind_battery_quarter_year():
     assert (res.status == S.OPTIMAL).all() and res.iters.max() <= 60
     ref = np.array([H.solve(L.wind_battery_raw(lam, cf, 847.0, b))[0] for b in (84.7, 211.75)])
     assert rel_err(res.obj, ref).max() < REL
+
+
+def test_determinism_and_permutation_invariance(wb):
+    """Size-independent properties at the full C2 size: the ticket dispatcher hands LPs to warps in a run-dependent
+    order, yet every LP's result depends on its own data only -- two runs agree bit for bit, and permuting the batch
+    permutes the results."""
+    t, sol = wb
+    lmp, cf, W, P = SC.c2(10000)
+    rp = TP.wind_battery_rparams(24, cf, W, P)[0]
+    a = sol.solve_host(lmp, rp)
+    b = sol.solve_host(lmp, rp)
+    assert np.array_equal(a.obj, b.obj) and np.array_equal(a.iters, b.iters) and np.array_equal(a.status, b.status)
+    perm = np.random.default_rng(0).permutation(10000)
+    c = sol.solve_host(np.ascontiguousarray(lmp[perm]), rp)
+    assert np.array_equal(c.obj, a.obj[perm]) and np.array_equal(c.iters, a.iters[perm])
+    # checksum of checksums: batch split in two halves solved separately
+    d1 = sol.solve_host(np.ascontiguousarray(lmp[:5000]), rp); d2 = sol.solve_host(np.ascontiguousarray(lmp[5000:]), rp)
+    assert np.array_equal(np.concatenate([d1.obj, d2.obj]), a.obj)
