@@ -880,11 +880,15 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         warps = (long long)((budget - off) / prob_bytes);
     }
     bool ws_mode = false;
-    if (warps < 1) {
-        // long horizons: the per-LP work region does not fit in shared memory -> same kernel, work regions in a global
-        // workspace (L2-resident sweeps; slower per LP, but a full-year T = 8736 LP runs at all)
+    if (warps <= 1) {
+        // the per-LP work region fills (or exceeds) the shared memory of an SM -> same kernel, work regions in a global
+        // workspace with kMaxWarps LPs in flight per SM.  A workspace warp is ~6x slower than a shared-memory warp (L2
+        // latency in the sweeps) but 14-16 of them beat the single shared-memory warp 2.4-2.6x at T = 168
+        // (profiles/ws_mode_sweep_r1.json); long horizons (full-year T = 8736) run only this way.
         ws_mode = true;
-        warps = 2;
+        hot_in_smem = 0; off = 16;
+        warps = kMaxWarps;
+        while (warps > 1 && (size_t)T->sm_count * (size_t)warps * prob_bytes > ((size_t)48 << 30)) warps /= 2;
     }
     if (const char *e = getenv("DSP_BAND_WS_WARPS")) {        // experiment switch: force the global-workspace mode
         const long long f = atoll(e);
@@ -1007,7 +1011,7 @@ int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, c
         dstride = K.Pr;
     }
     // templates that run in global-workspace mode share ONE workspace: no concurrent chunk kernels for them
-    const bool ws_template = 16 + (size_t)K.prob_doubles * 8 > (size_t)T->smem_optin;
+    const bool ws_template = 16 + 2 * (size_t)K.prob_doubles * 8 > (size_t)T->smem_optin;      // launch_batch: warps <= 1
     const int nchunk = ws_template ? 1 : (int)std::min<int64_t>(in_pinned ? 2 : 8, std::max<int64_t>(1, N / 2048));
     const int64_t per = (N + nchunk - 1) / nchunk;
     for (int c = 0; c < nchunk; ++c) {
