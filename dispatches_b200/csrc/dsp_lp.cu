@@ -880,11 +880,11 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         warps = (long long)((budget - off) / prob_bytes);
     }
     bool ws_mode = false;
-    if (warps <= 1) {
-        // the per-LP work region fills (or exceeds) the shared memory of an SM -> same kernel, work regions in a global
-        // workspace with kMaxWarps LPs in flight per SM.  A workspace warp is ~6x slower than a shared-memory warp (L2
-        // latency in the sweeps) but 14-16 of them beat the single shared-memory warp 2.4-2.6x at T = 168
-        // (profiles/ws_mode_sweep_r1.json); long horizons (full-year T = 8736) run only this way.
+    if (warps <= 3) {
+        // at most three work regions fit the shared memory of an SM -> same kernel, work regions in a global workspace
+        // with kMaxWarps LPs in flight per SM.  A workspace warp is ~6x slower than a shared-memory warp (L2 latency in
+        // the sweeps), but 14-16 of them beat one shared-memory warp 2.4-2.6x (T = 168) and two or three 1.3x
+        // (T = 96, T = 48 bidder; profiles/ws_mode_sweep*_r1.json); long horizons (T = 8736) run only this way.
         ws_mode = true;
         hot_in_smem = 0; off = 16;
         warps = kMaxWarps;
@@ -1011,7 +1011,7 @@ int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, c
         dstride = K.Pr;
     }
     // templates that run in global-workspace mode share ONE workspace: no concurrent chunk kernels for them
-    const bool ws_template = 16 + 2 * (size_t)K.prob_doubles * 8 > (size_t)T->smem_optin;      // launch_batch: warps <= 1
+    const bool ws_template = 16 + 4 * (size_t)K.prob_doubles * 8 > (size_t)T->smem_optin;      // launch_batch: warps <= 3
     const int nchunk = ws_template ? 1 : (int)std::min<int64_t>(in_pinned ? 2 : 8, std::max<int64_t>(1, N / 2048));
     const int64_t per = (N + nchunk - 1) / nchunk;
     for (int c = 0; c < nchunk; ++c) {
