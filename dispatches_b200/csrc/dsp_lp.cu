@@ -65,6 +65,8 @@ struct KParams {
     double *ws;                   // non-null: per-warp work regions live in this global-memory workspace (long horizons)
     int prob_doubles;             // per-warp work-region doubles
     int prob_off;                 // byte offset of the first per-warp region
+    int band_doubles;             // doubles of the (dy, Mb) tail of a work region: what the LDL' / substitution sweeps touch
+    int hybrid;                   // workspace mode with the (dy, Mb) tail in shared memory (sweeps at shared-memory latency)
 };
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -485,7 +487,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) dsp_ipm_band_kernel(const K
     W.x = base; W.z = W.x + n; W.c = W.z + n; W.rd = W.c + n; W.d = W.rd + n; W.dx = W.d + n; W.cor = W.dx + n; W.rx = W.cor + n;
     W.s = W.rx + n; W.wv = W.s + nb; W.u = W.wv + nb; W.ru = W.u + nb; W.cors = W.ru + nb; W.rs = W.cors + nb;
     W.y = W.rs + nb; W.b = W.y + m; W.rp = W.b + m;
-    W.dy = W.rp + m + BW;
+    double *band0 = W.rp + m;
+    if (WS && P.hybrid) band0 = (double *)(smem + P.prob_off) + (size_t)warp * P.band_doubles;
+    W.dy = band0 + BW;
     W.Mb = W.dy + m + BW + BW * (BW + 1);
     for (;;) {
         unsigned long long t = 0;
@@ -779,7 +783,9 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     if (rc) return DSP_E_CUDA;
     CK(cudaMalloc((void **)&T->ticket, 16 * sizeof(unsigned long long)));
     T->dev_allocs.push_back(T->ticket);
-    K.prob_doubles = 8 * n + 6 * nb + 3 * m + (m + 2 * wt) + (m + 2 * wt) * (wt + 1);
+    K.band_doubles = (m + 2 * wt) + (m + 2 * wt) * (wt + 1);
+    K.prob_doubles = 8 * n + 6 * nb + 3 * m + K.band_doubles;
+    K.hybrid = 0;
     CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
@@ -790,6 +796,11 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaStreamCreateWithFlags(&T->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&T->stream2, cudaStreamNonBlocking));
     *out = T;
@@ -833,6 +844,44 @@ void dsp_lp_template_destroy(dsp_template *T) {
     delete T;
 }
 
+// Geometry of a band-kernel launch: one persistent CTA per SM, `warps` LPs in flight per CTA, and one of three
+// placements of the per-LP work region (measured on the B200: profiles/band_modes_r1.json, ws_mode_sweep*_r1.json):
+//   smem    everything in shared memory: fastest warp, but only as many LPs per SM as regions fit;
+//   hybrid  the (dy, Mb) tail -- all that the LDL' / substitution sweeps touch -- in shared memory, the element-wise
+//           vectors in a global workspace (coalesced streaming through L2): a warp runs at ~0.3-0.45 of the smem speed;
+//   ws      everything in the global workspace, kMaxWarps LPs per SM: a warp runs at ~1/6 of the smem speed (L2 latency
+//           in the sweeps); the only choice for long horizons (T = 8736).
+struct BandGeom { long long warps; int hot_in_smem; size_t off; bool ws; int hybrid; };
+
+BandGeom band_geometry(const dsp_template *T, const KParams &K) {
+    const size_t prob_bytes = (size_t)K.prob_doubles * 8, band_bytes = (size_t)K.band_doubles * 8;
+    const size_t budget = (size_t)T->smem_optin;
+    BandGeom g{0, 1, 16 + (size_t)K.hot_bytes, false, 0};
+    long long smem_warps = budget > g.off ? (long long)((budget - g.off) / prob_bytes) : 0;
+    if (smem_warps < 4) {   // template too large to stage next to the work regions: read it through L2
+        g.hot_in_smem = 0;
+        g.off = 16;
+        smem_warps = (long long)((budget - g.off) / prob_bytes);
+    }
+    const long long hybrid_warps = band_bytes + 16 <= budget ? std::min<long long>(kMaxWarps, (long long)((budget - 16) / band_bytes)) : 0;
+    enum { M_SMEM, M_HYBRID, M_WS } mode = smem_warps >= 7 ? M_SMEM : hybrid_warps >= 6 ? M_HYBRID : smem_warps >= 4 ? M_SMEM : M_WS;
+    if (const char *e = getenv("DSP_BAND_MODE")) {            // experiment switch
+        if (!strcmp(e, "ws")) mode = M_WS;
+        else if (!strcmp(e, "hybrid") && hybrid_warps >= 1) mode = M_HYBRID;
+        else if (!strcmp(e, "smem") && smem_warps >= 1) mode = M_SMEM;
+    }
+    if (mode == M_SMEM) {
+        g.warps = smem_warps;
+    } else {
+        g.ws = true; g.hot_in_smem = 0; g.off = 16;
+        g.hybrid = mode == M_HYBRID;
+        g.warps = g.hybrid ? hybrid_warps : kMaxWarps;
+        while (g.warps > 1 && (size_t)T->sm_count * (size_t)g.warps * prob_bytes > ((size_t)48 << 30)) g.warps /= 2;
+    }
+    g.warps = std::min<long long>(g.warps, kMaxWarps);
+    return g;
+}
+
 static int launch_batch(const dsp_template *T, int64_t N, const double *cparams, const double *rparams,
                         int64_t rparams_stride, const dsp_opts *opts, double *obj, int32_t *status, int32_t *iters,
                         double *x, double *y, void *cuda_stream, unsigned long long *ticket) {
@@ -868,33 +917,13 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         g_err = "dsp_lp_solve_batch: the template has no stage descriptor";
         return DSP_E_ARG;
     }
-    // geometry: one persistent CTA per SM; as many warps (= LPs in flight) as shared memory allows
     const size_t prob_bytes = (size_t)K.prob_doubles * 8;
-    const size_t budget = (size_t)T->smem_optin;
-    int hot_in_smem = 1;
-    size_t off = 16 + (size_t)K.hot_bytes;
-    long long warps = budget > off ? (long long)((budget - off) / prob_bytes) : 0;
-    if (warps < 4) {   // template too large to stage: read it through L2
-        hot_in_smem = 0;
-        off = 16;
-        warps = (long long)((budget - off) / prob_bytes);
-    }
-    bool ws_mode = false;
-    if (warps <= 3) {
-        // at most three work regions fit the shared memory of an SM -> same kernel, work regions in a global workspace
-        // with kMaxWarps LPs in flight per SM.  A workspace warp is ~6x slower than a shared-memory warp (L2 latency in
-        // the sweeps), but 14-16 of them beat one shared-memory warp 2.4-2.6x (T = 168) and two or three 1.3x
-        // (T = 96, T = 48 bidder; profiles/ws_mode_sweep*_r1.json); long horizons (T = 8736) run only this way.
-        ws_mode = true;
-        hot_in_smem = 0; off = 16;
-        warps = kMaxWarps;
-        while (warps > 1 && (size_t)T->sm_count * (size_t)warps * prob_bytes > ((size_t)48 << 30)) warps /= 2;
-    }
-    if (const char *e = getenv("DSP_BAND_WS_WARPS")) {        // experiment switch: force the global-workspace mode
-        const long long f = atoll(e);
-        if (f > 0) { ws_mode = true; warps = f; hot_in_smem = 0; off = 16; }
-    }
-    warps = std::min<long long>(warps, kMaxWarps);
+    const size_t band_bytes = (size_t)K.band_doubles * 8;
+    const BandGeom geom = band_geometry(T, K);
+    long long warps = geom.warps;
+    const int hot_in_smem = geom.hot_in_smem, hybrid = geom.hybrid;
+    const size_t off = geom.off;
+    const bool ws_mode = geom.ws;
     long long ctas = std::min<long long>(T->sm_count, (N + warps - 1) / warps);
     // spread a small batch over all SMs
     if (ctas < T->sm_count && N > ctas) {
@@ -915,8 +944,9 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
             T->ws_bytes = need;
         }
         K.ws = T->ws;
-        smem = 16;
+        smem = hybrid ? off + (size_t)warps * band_bytes : 16;
     }
+    K.hybrid = hybrid;
     CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
     switch (K.w) {
         case 1: if (ws_mode) dsp_ipm_band_kernel<1, true, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
@@ -1011,7 +1041,7 @@ int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, c
         dstride = K.Pr;
     }
     // templates that run in global-workspace mode share ONE workspace: no concurrent chunk kernels for them
-    const bool ws_template = 16 + 4 * (size_t)K.prob_doubles * 8 > (size_t)T->smem_optin;      // launch_batch: warps <= 3
+    const bool ws_template = band_geometry(T, K).ws;
     const int nchunk = ws_template ? 1 : (int)std::min<int64_t>(in_pinned ? 2 : 8, std::max<int64_t>(1, N / 2048));
     const int64_t per = (N + nchunk - 1) / nchunk;
     for (int c = 0; c < nchunk; ++c) {
