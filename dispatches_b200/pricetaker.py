@@ -10,7 +10,8 @@ Same names and argument meaning as the reference functions; the only extension i
 
 Where the reference builds a Pyomo MultiPeriodModel and calls SolverFactory("cbc").solve(m) once per signal,
 these build (and cache) one LPTemplate per (flowsheet, T) and hand the whole batch to the CUDA solver.
-``design_opt`` other than False is not on the GPU path yet (dense border in the KKT system).
+``design_opt=True`` (battery size; with ``extant_wind=False`` also the wind size, for one capacity-factor series per call)
+and ``design_opt="PEM"`` run on the same path: capacity columns are kept per period with link equalities (banded).
 """
 from __future__ import annotations
 
@@ -114,10 +115,10 @@ def _lmps(input_params, T):
 def wind_battery_optimize(n_time_points, input_params, verbose=False, want_solution=True):
     T = int(n_time_points)
     design = bool(input_params.get("design_opt", False))
-    if design and not input_params.get("extant_wind", True):
-        raise NotImplementedError("design_opt with a free wind size is not on the batched GPU path")
     lmp = _lmps(input_params, T)
     cf = _capacity_factors(input_params, T)
+    if design and not input_params.get("extant_wind", True):
+        return _wind_battery_free_wind(T, lmp, cf, input_params, verbose)
     sol = get_solver("wind_battery_design" if design else "wind_battery", T,
                      extant_wind=bool(input_params.get("extant_wind", True)))
     want_solution = want_solution or design          # the optimal battery size is read from the solution
@@ -137,6 +138,31 @@ def wind_battery_optimize(n_time_points, input_params, verbose=False, want_solut
     if design:                                        # optimised size: value(m.battery_system_capacity)
         sizes["batt_kw"] = xm[:, sol.t.col_names.index("blk[0].fs.battery.nameplate_power")].copy()
     return PriceTakerResult("wind_battery", T, lmp, r.obj, r.status, r.iters, xm, sol.t.col_names, sizes)
+
+
+def _wind_battery_free_wind(T, lmp, cf, input_params, verbose):
+    """design_opt=True, extant_wind=False: battery and wind size are decisions (wind_battery_LMP.py:209-219).  cf_t
+    multiplies the wind-capacity column, so the capacity-factor series is part of the template: one series per call,
+    batched over the LMP scenarios."""
+    cf = np.asarray(cf, float)
+    if cf.ndim != 1:
+        if not np.all(cf == cf[:1]):
+            raise NotImplementedError("design_opt with a free wind size: one capacity-factor series per call "
+                                      "(cf_t enters the constraint matrix, which the batch shares)")
+        cf = cf[0]
+    key = ("wind_battery_design_free_wind", T, cf.tobytes(), float(input_params.get("wind_mw_ub", 10000.0)))
+    if key not in _SOLVERS:
+        _SOLVERS[key] = BatchLPSolver(TP.wind_battery_design_free_wind(T, cf, key[3]))
+    sol = _SOLVERS[key]
+    r = sol.solve_host(lmp, None, want_x=True)
+    if verbose:
+        print(f"b200ipm: {lmp.shape[0]} LPs, iterations mean {r.iters.mean():.1f} max {r.iters.max()}, "
+              f"non-optimal {(r.status != OPTIMAL).sum()}")
+    xm = sol.to_model_space(r.x)
+    names = sol.t.col_names
+    sizes = dict(wind_kw=xm[:, names.index("blk[0].fs.windpower.system_capacity")].copy(),      # value(m.wind_system_capacity)
+                 batt_kw=xm[:, names.index("blk[0].fs.battery.nameplate_power")].copy())         # value(m.battery_system_capacity)
+    return PriceTakerResult("wind_battery", T, lmp, r.obj, r.status, r.iters, xm, names, sizes)
 
 
 def wind_battery_pem_optimize(time_points, input_params, verbose=False, want_solution=True):

@@ -134,6 +134,53 @@ def wind_battery_design(T: int, extant_wind: bool = True) -> LPTemplate:
     return B.build()
 
 
+def wind_battery_design_free_wind(T: int, cf, wind_mw_ub: float = 10000.0) -> LPTemplate:
+    """wind_battery_optimize with design_opt=True and extant_wind=False (wind_battery_LMP.py:209-219, :256-263): battery
+    AND wind size are decisions.  The wind row  electricity <= system_capacity * cf_t  (wind_power.py:120-122) puts cf_t
+    into the constraint matrix, which the batch shares -- so this template is built for ONE capacity-factor series
+    (the reference's design runs use the site's series with many price signals) and batched over LMPs only.
+    wind_system_capacity >= system_capacity[t] (:218) is tight at the optimum (no other cost on system_capacity[t]); as
+    for the battery, one capacity column per period + link equalities keeps the matrix banded.
+    cparams = lmp[T];  rparams = [] ."""
+    cf = np.asarray(cf, float)
+    assert cf.shape == (T,)
+    B = TemplateBuilder(f"wind_battery_design_free_wind_T{T}", Pc=T, Pr=0)
+    ann = 52.0 / (T / 168.0)
+    k_rev = -1e-5 * PA * ann * 1e-3
+    cap = BATT_CAP_COST_KW + BATT_CAP_COST_KWH * DURATION
+    g, i, o, s, e, Pn, Wn = {}, {}, {}, {}, {}, {}, {}
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        g[t] = B.var(p + "splitter.grid_elec[0]")
+        i[t] = B.var(p + "battery.elec_in[0]")
+        o[t] = B.var(p + "battery.elec_out[0]")
+        s[t] = B.var(p + "battery.state_of_charge[0]", fix=(0.0 if t == T - 1 else None))
+        e[t] = B.var(p + "battery.energy_throughput[0]")
+        Pn[t] = B.var(p + "battery.nameplate_power")
+        Wn[t] = B.var(p + "windpower.system_capacity", ub=(wind_mw_ub * 1e3 if t == 0 else None))     # :209
+        B.cost(g[t], (0.0, {t: k_rev})); B.cost(o[t], (0.0, {t: k_rev}))
+    B.cost(Pn[0], 1e-5 * (cap + PA * ann * T * BATT_OP_COST / 8760.0))
+    B.cost(Wn[0], 1e-5 * (WIND_CAP_COST + PA * ann * T * WIND_OP_COST / 8760.0))
+    for t in range(T):
+        row = {s[t]: 1.0, i[t]: -ETA_C, o[t]: 1.0 / ETA_D}
+        if t > 0:
+            row[s[t - 1]] = -1.0
+        B.eq(f"soc[{t}]", row)
+        row = {e[t]: 1.0, i[t]: -0.5, o[t]: -0.5}
+        if t > 0:
+            row[e[t - 1]] = -1.0
+        B.eq(f"throughput[{t}]", row)
+        B.le(f"power_bound_in[{t}]", {i[t]: 1.0, Pn[t]: -1.0})
+        B.le(f"power_bound_out[{t}]", {o[t]: 1.0, Pn[t]: -1.0})
+        B.le(f"soc_bound[{t}]", {s[t]: 1.0, e[t]: DEGRADATION, Pn[t]: -DURATION})
+        B.le(f"wind[{t}]", {g[t]: 1.0, i[t]: 1.0, Wn[t]: -float(cf[t])})
+        if t < T - 1:
+            B.eq(f"link_nameplate[{t}]", {Pn[t]: 1.0, Pn[t + 1]: -1.0})
+            B.eq(f"link_wind[{t}]", {Wn[t]: 1.0, Wn[t + 1]: -1.0})
+    B.meta.update(kind="wind_battery_design_free_wind", T=T, ann=ann)
+    return B.build(equilibrate=True)
+
+
 def wind_battery_rparams(T, cf, wind_mw, batt_mw, pem_mw=None):
     """rparams rows for wind_battery / wind_battery_pem: cf [N,T] or [T]; sizes scalar or [N]."""
     cf = np.atleast_2d(np.asarray(cf, float))

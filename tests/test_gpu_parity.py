@@ -325,6 +325,22 @@ def test_design_opt_border_column():
     assert np.all(res.sizes["batt_kw"][~big] < 1e3 * 1.01 + 50.0)
 
 
+def test_design_opt_free_wind():
+    """design_opt=True with extant_wind=False through the reference-shaped API: wind and battery size are decisions
+    (wind_battery_LMP.py:209-219); objective and optimal sizes against the raw oracle LP."""
+    lmp, cf, W, P = SC.c2(24)
+    scale = np.where(np.arange(24) % 2 == 1, 20.0, 1.0)[:, None]
+    ip = {"wind_mw": W, "wind_mw_ub": 10000, "batt_mw": P, "design_opt": True, "extant_wind": False,
+          "wind_resource": cf, "DA_LMPs": lmp * scale}
+    res = PT.wind_battery_optimize(24, ip)
+    assert np.all(res.status == S.OPTIMAL)
+    for k in range(0, 24, 3):
+        ref, xr = H.solve(L.wind_battery_raw(lmp[k] * scale[k, 0], cf, W, P, design_opt=True, extant_wind=False))
+        assert rel_err(res.obj[k], ref) < REL
+        raw = L.wind_battery_raw(lmp[k] * scale[k, 0], cf, W, P, design_opt=True, extant_wind=False)
+        assert res.sizes["wind_kw"][k] == pytest.approx(xr[raw.meta["Wc"]], rel=1e-4, abs=50.0)
+
+
 def test_design_opt_pem_mode():
     """design_opt="PEM" (run_pricetaker_wind_PEM.py:36-37, pem_ratio None): PEM size optimised, battery fixed at 0."""
     lmp, cf, W, P = SC.c2(40)

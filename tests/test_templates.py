@@ -131,3 +131,21 @@ def test_nuclear_report_enumeration_presolve_equals_the_full_lp():
             obj, x = H.solve(L.nuclear_report_raw(lmp, hp, pc * 400.0, pem_capex=400.0))
             assert res["net_npv"][f"{i1}{i2}"] == pytest.approx(-obj / 1e6, rel=1e-9)
     assert 0.0 <= res["pem_cap_factor"]["11"] <= 1.0 and res["solver_stat"]["00"] == "optimal"
+
+
+def test_design_free_wind_matches_raw_oracle():
+    """design_opt=True, extant_wind=False: battery and wind size free (wind_battery_LMP.py:209-219); cf_t sits in A."""
+    lmp, cf, W, P = SC.c2(6)
+    t = TP.wind_battery_design_free_wind(24, cf)
+    assert t.w <= 16 and t.Pr == 0
+    for k in range(6):
+        for scale in (1.0, 20.0):                       # ordinary prices: build nothing; 20x prices: build to the 10 GW cap
+            c, b, u, kk = t.instantiate(lmp[k] * scale, np.zeros(0))
+            r = None
+            for opts in (dict(primal_feasibility_tolerance=1e-10, dual_feasibility_tolerance=1e-10), {}):
+                r = linprog(c, A_eq=t.A, b_eq=b, bounds=[(0, None if not np.isfinite(v) else v) for v in u], method="highs-ds", options=opts)
+                if r.status == 0:
+                    break
+            assert r.status == 0, r.message
+            ref, _ = H.solve(L.wind_battery_raw(lmp[k] * scale, cf, W, P, design_opt=True, extant_wind=False))
+            assert r.fun + kk == pytest.approx(ref, rel=1e-9, abs=1e-6)
