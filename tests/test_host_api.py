@@ -17,8 +17,11 @@ def reference_params(lmp, cf, W, P, **kw):
 
 def test_design_opt_is_refused_not_silently_fixed():
     lmp, cf, W, P = SC.c2(2)
+    # a free wind size needs ONE capacity-factor series per call (cf_t enters the shared constraint matrix)
+    params = reference_params(lmp, cf, W, P, design_opt=True, extant_wind=False)
+    params["wind_resource"] = np.stack([cf, 0.5 * cf])
     with pytest.raises(NotImplementedError):
-        PT.wind_battery_optimize(24, reference_params(lmp, cf, W, P, design_opt=True, extant_wind=False))
+        PT.wind_battery_optimize(24, params)
     with pytest.raises(NotImplementedError):
         PT.wind_battery_pem_optimize(24, reference_params(lmp, cf, W, P, design_opt=True, pem_mw=100, h2_price_per_kg=2))
 
