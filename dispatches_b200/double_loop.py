@@ -25,7 +25,7 @@ from .solver import BatchLPSolver, OPTIMAL
 _SOLVERS = {}
 
 
-_FAMILIES = {"wind_battery": TP.wind_battery_operation, "nuclear": TP.nuclear_operation}
+_FAMILIES = {"wind_battery": TP.wind_battery_operation, "nuclear": TP.nuclear_operation, "wind_pem": TP.wind_pem_operation}
 
 
 def _lp_solve(mode, T, cparams, rparams, n_tracking_hour=1, options=None, family="wind_battery"):
@@ -44,7 +44,7 @@ _COLS = dict(grid="blk[{t}].fs.splitter.grid_elec[0]", batt_in="blk[{t}].fs.batt
              under="power_underdelivered_kw[{t}]", over="power_overdelivered_kw[{t}]",
              da="day_ahead_power_kw[{t}]", underbid="real_time_underbid_power_kw[{t}]",
              pem="blk[{t}].fs.pem.electricity[0]", pipeline="blk[{t}].fs.h2_tank.outlet_to_pipeline.flow_mol[0]",
-             holdup="blk[{t}].fs.h2_tank.tank_holdup[0]")
+             holdup="blk[{t}].fs.h2_tank.tank_holdup[0]", pem_cap="pem_system_capacity[{t}]")
 
 
 def _columns(template, xm, T):
@@ -237,6 +237,96 @@ class MultiPeriodWindBattery:
     def write_results(self, path):
         import pandas as pd
         pd.concat(self.result_list).to_csv(path, index=False)                                                  # :344
+
+    @property
+    def power_output(self):
+        return "P_T"
+
+    @property
+    def total_cost(self):
+        return ("tot_cost", 1)
+
+
+class MultiPeriodWindPEM:
+    """wind_PEM_double_loop.py:103-330 (wind + PEM, battery size 0).  Only the Tracker solves an LP with this model; the
+    reference's bidder for it (PEM_parametrized_bidder.py) derives its bids from forecasts without optimisation."""
+
+    def __init__(self, model_data, wind_capacity_factors, wind_pmax_mw=200.0, pem_pmax_mw=25.0):
+        self.model_data = model_data
+        if wind_capacity_factors is None:
+            raise ValueError("Please provide wind capacity factors.")                                       # :125-126
+        self._wind_capacity_factors = np.atleast_2d(np.asarray(wind_capacity_factors, float))
+        N = self._wind_capacity_factors.shape[0]
+        sizes = np.broadcast_arrays(np.zeros(N), wind_pmax_mw, pem_pmax_mw)
+        self.N = sizes[0].shape[0]
+        if N == 1 and self.N > 1:
+            self._wind_capacity_factors = np.repeat(self._wind_capacity_factors, self.N, axis=0)
+        self._wind_pmax_mw, self._pem_pmax_mw = (np.array(x, float) for x in sizes[1:])
+        self.result_list = []
+
+    def populate_model(self, b, horizon):
+        b.horizon, b._time_idx = horizon, 0
+        b.cf = self._wind_capacity_factors[:, 0:horizon].copy()
+        return b
+
+    def update_model(self, b, realized_h2_sales):
+        b._time_idx = b._time_idx + min(len(realized_h2_sales), 24)                                         # :196-197
+        b.cf = self._get_capacity_factors(b)
+
+    def _get_capacity_factors(self, b):
+        ans = self._wind_capacity_factors[:, b._time_idx:b._time_idx + b.horizon]
+        if ans.shape[1] < b.horizon:                                                                         # :219-220
+            ans = np.concatenate([ans, self._wind_capacity_factors[:, 0:b.horizon - ans.shape[1]]], axis=1)
+        return ans
+
+    def _lp(self, b, mode, da=None, rt=None, signal_mw=None, n_tracking_hour=1, options=None):
+        if mode != "tracker":
+            raise NotImplementedError("MultiPeriodWindPEM is bid with the parametrised bidder (no LP); only the Tracker solves one")
+        T = b.horizon
+        W = self._wind_pmax_mw[:, None] * 1e3
+        sig = np.broadcast_to(np.atleast_2d(np.asarray(signal_mw, float)), (self.N, T))
+        rp = np.concatenate([b.cf * W, W, sig], axis=1)
+        obj, status, cols = _lp_solve(mode, T, np.ones((self.N, 1)), rp, n_tracking_hour, options, "wind_pem")
+        b.sol = cols
+        b.P_T = cols["grid"] * 1e-3                                                                          # :168
+        b.wind_waste = cols["waste"]                                                                         # :169 (kW)
+        b.tot_cost = (W * TP.WIND_OP_COST / 8760.0 + cols["pem_cap"] * TP.PEM_OP_COST / 8760.0
+                      + TP.PEM_VAR_COST * cols["pem"] + b.wind_waste)                                        # :170-172
+        return obj, status, cols
+
+    @staticmethod
+    def get_last_delivered_power(b, last_implemented_time_step):
+        return b.P_T[:, last_implemented_time_step]
+
+    @staticmethod
+    def get_implemented_profile(b, last_implemented_time_step):
+        k = TP.PEM_ELEC_TO_MOL / TP.H2_MOLS_PER_KG * 3600.0
+        return {"realized_h2_sales": deque(b.sol["pem"][:, t] * k for t in range(last_implemented_time_step + 1))}   # :253-256
+
+    def record_results(self, b, date=None, hour=None, **kwargs):
+        """Rows of the reference's table (:265-320)."""
+        import pandas as pd
+        k = TP.PEM_ELEC_TO_MOL / TP.H2_MOLS_PER_KG * 3600.0
+        rows = []
+        for n in range(self.N):
+            for t in range(b.horizon):
+                row = {"Generator": self.model_data.gen_name, "Date": date, "Hour": hour, "Horizon [hr]": int(t),
+                       "Total Wind Generation [MW]": round(float((b.sol["grid"][n, t] + b.sol["pem"][n, t]) * 1e-3), 2),
+                       "Total Power Output [MW]": round(float(b.P_T[n, t]), 2),
+                       "Wind Power Output [MW]": round(float(b.sol["grid"][n, t] * 1e-3), 2),
+                       "Wind to PEM [MW]": round(float(b.sol["pem"][n, t] * 1e-3), 2),
+                       "Wind Curtailment [MW]": round(float(b.wind_waste[n, 0]), 2),       # the reference reads index 0, in kW (:302)
+                       "Hydrogen Sales [kg]": round(float(b.sol["pem"][n, t] * k), 2),
+                       "Total Cost [$]": round(float(b.tot_cost[n, t]), 2)}
+                if self.N > 1:
+                    row["Simulation"] = n
+                row.update(kwargs)
+                rows.append(row)
+        self.result_list.append(pd.DataFrame(rows))
+
+    def write_results(self, path):
+        import pandas as pd
+        pd.concat(self.result_list).to_csv(path, index=False)
 
     @property
     def power_output(self):

@@ -463,3 +463,35 @@ def nuclear_operation(T: int, mode: str, n_tracking_hour: int = 1, np_capacity=N
                 B.eq(f"day_ahead_power_ub[{t}]", {xp[t]: -1.0, ub: 1.0, sp_: -1.0}, (-E, {iD + t: 1e3}))
     B.meta.update(kind="nuclear_operation", mode=mode, T=T, E=E, n_tracking_hour=n_tracking_hour)
     return B.build(equilibrate=True)
+
+
+def wind_pem_operation(T: int, mode: str = "tracker", n_tracking_hour: int = 1) -> LPTemplate:
+    """MultiPeriodWindPEM's operation model (wind_PEM_double_loop.py:25-172; battery size 0) under the Tracker objective.
+    pem_system_capacity is a free non-negative Var of that model (:69-73): one copy per period + link equalities (banded).
+    Its bidder is parametrised (no LP), so "tracker" is the only mode.
+    rparams = [wind_kw*cf_t (T), wind_kw, dispatch_MW_t (T)];  cparams = [wind_waste weight ($/kW, 1 in the reference)]"""
+    assert mode == "tracker"
+    iW, iD = T, T + 1
+    B = TemplateBuilder(f"wind_pem_tracker_T{T}", Pc=1, Pr=2 * T + 1)
+    g, pe, waste, cap = {}, {}, {}, {}
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        g[t] = B.var(p + "splitter.grid_elec[0]")
+        pe[t] = B.var(p + "pem.electricity[0]")
+        waste[t] = B.var(f"wind_waste_kw[{t}]")
+        cap[t] = B.var(f"pem_system_capacity[{t}]")
+        B.cost(waste[t], (0.0, {0: 1.0}))                                    # :172
+        B.cost(pe[t], PEM_VAR_COST)
+        B.cost(cap[t], PEM_OP_COST / 8760.0)                                 # :171, once per period
+    B.obj_const((0.0, {iW: T * WIND_OP_COST / 8760.0}))                       # :170
+    for t in range(T):
+        B.eq(f"wind[{t}]", {g[t]: 1.0, pe[t]: 1.0, waste[t]: 1.0}, (0.0, {t: 1.0}))
+        B.le(f"pem_max_p[{t}]", {pe[t]: 1.0, cap[t]: -1.0})                  # :73
+        un = B.var(f"power_underdelivered_kw[{t}]"); ov = B.var(f"power_overdelivered_kw[{t}]")
+        pen = LARGE_PENALTY if t < n_tracking_hour else LARGE_PENALTY / max(1, T - n_tracking_hour)
+        B.cost(un, pen * 1e-3); B.cost(ov, pen * 1e-3)
+        B.eq(f"tracking_dispatch[{t}]", {g[t]: 1.0, un: 1.0, ov: -1.0}, (0.0, {iD + t: 1e3}))
+        if t < T - 1:
+            B.eq(f"link_pem_capacity[{t}]", {cap[t]: 1.0, cap[t + 1]: -1.0})
+    B.meta.update(kind="wind_pem_operation", mode=mode, T=T, n_tracking_hour=n_tracking_hour)
+    return B.build()

@@ -28,7 +28,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from .lp_models import (_Builder, BATT_CAP_COST_KW, DEGRADATION, ETA_C, ETA_D, WIND_OP_COST, nuclear_blocks, nuclear_operating_cost)
+from .lp_models import (_Builder, BATT_CAP_COST_KW, DEGRADATION, ETA_C, ETA_D, PEM_ELEC_TO_MOL, PEM_OP_COST, PEM_VAR_COST, WIND_OP_COST,
+                        nuclear_blocks, nuclear_operating_cost)
 
 BATT_REP_COST_KWH = BATT_CAP_COST_KW * 0.5 / 4.0     # load_parameters.py:48
 WASTE_PENALTY = 1e3                                  # wind_battery_double_loop.py:165
@@ -160,6 +161,41 @@ def nuclear_bidder_raw(da, rt, holdup0=0.0, h2_price=4.0, da_dispatch=None, **kw
         for j, a in cost[t][0].items():
             B.cost(j, a)
     return B.finish(dict(kind="nuclear_bidder", T=H, v=v))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# wind + PEM: MultiPeriodWindPEM (case_studies/renewables_case/wind_PEM_double_loop.py:25-260), battery size 0
+#   :56-82   transform_design_model_to_operation_model: wind size fixed, pem.electricity <= pem_system_capacity with
+#            pem_system_capacity a (free, non-negative) Var of the model, periodic row deactivated
+#   :163-172 P_T = grid_elec * 1e-3 ; wind_waste in kW ; tot_cost = wind O&M + pem_system_capacity * pem O&M / 8760
+#            + pem var cost + wind_waste
+# Its bidder (PEM_parametrized_bidder.py) computes bids from forecasts without an optimisation; the Tracker LP is the
+# only LP and is pinned by tests/test_wind_PEM_double_loop.py:55-121 (wind, delivered power, PEM power).
+# ---------------------------------------------------------------------------------------------------------------
+def wind_pem_tracker_raw(dispatch, cf, wind_mw=200.0, pem_mw=25.0, n_tracking_hour=1):
+    dispatch = np.asarray(dispatch, float); H = dispatch.size
+    B = _Builder(); v = {}
+    C = wind_mw * 1e3
+    v["Pc"] = B.var("pem_system_capacity")                                   # :69 (initialised at pem_mw, not fixed)
+    for t in range(H):
+        p = f"blk[{t}].fs."
+        v["w", t] = B.var(p + "windpower.electricity[0]")
+        v["g", t] = B.var(p + "splitter.grid_elec[0]")
+        v["pe", t] = B.var(p + "pem.electricity[0]")
+        v["h", t] = B.var(p + "pem.outlet.flow_mol[0]")
+        B.le({v["w", t]: 1.0}, C * cf[t])                                    # wind_power.py:120-122
+        B.eq({v["w", t]: 1.0, v["g", t]: -1.0, v["pe", t]: -1.0})            # splitter + arcs (battery size 0)
+        B.eq({v["h", t]: 1.0, v["pe", t]: -PEM_ELEC_TO_MOL})                 # pem_electrolyzer.py:111-114
+        B.le({v["pe", t]: 1.0, v["Pc"]: -1.0})                               # :73
+        v["under", t] = B.var(f"power_underdelivered[{t}]")
+        v["over", t] = B.var(f"power_overdelivered[{t}]")
+        B.eq({v["g", t]: 1e-3, v["under", t]: 1.0, v["over", t]: -1.0}, dispatch[t])
+        pen = LARGE_PENALTY if t < n_tracking_hour else LARGE_PENALTY / max(1, H - n_tracking_hour)
+        B.cost(v["under", t], pen); B.cost(v["over", t], pen)
+        # tot_cost[t] (:169-172); wind_waste[t] = C*cf - w in kW enters with weight 1
+        B.cost(v["Pc"], PEM_OP_COST / 8760.0); B.cost(v["pe", t], PEM_VAR_COST); B.cost(v["w", t], -1.0)
+        B.c0 += C * WIND_OP_COST / 8760.0 + C * cf[t]
+    return B.finish(dict(kind="wind_pem_tracker", T=H, v=v))
 
 
 def backcast(historical, hour, horizon, n_samples):

@@ -18,7 +18,8 @@ Writes
   double_loop_golden.json -- inputs and known answers of the reference's double-loop tests
                            (case_studies/renewables_case/tests/test_multiperiod_wind_battery_doubleloop.py:78-111 tracker,
                            :168-175 self-schedule bids, :245-252 thermal-generator bid prices): the first 48 h of
-                           309_WIND_1-RTCF / 309_DALMP / 309_RTLMP and the asserted vectors (read with ``ast``).
+                           309_WIND_1-RTCF / 309_DALMP / 309_RTLMP and the asserted vectors (read with ``ast``); the wind + PEM
+                           tracker's known answers (tests/test_wind_PEM_double_loop.py:55-121).
 No reference SOURCE is copied: only numeric data and test constants.
 """
 import ast
@@ -44,7 +45,19 @@ def double_loop():
                     lists[fn.name, node.targets[0].id] = [float(v) for v in ast.literal_eval(node.value)]
                 except (ValueError, TypeError):
                     pass
+    tree2 = ast.parse(open(rc / "tests" / "test_wind_PEM_double_loop.py").read())
+    for fn in [n for n in tree2.body if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.Assign) and isinstance(node.targets[0], ast.Name) and isinstance(node.value, ast.List):
+                try:
+                    lists["wind_pem", fn.name, node.targets[0].id] = [float(v) for v in ast.literal_eval(node.value)]
+                except (ValueError, TypeError):
+                    pass
     gold = dict(
+        # test_wind_PEM_double_loop.py:55-121: tracker of the wind + PEM model (200 MW wind, PEM 25 MW)
+        wind_pem_tracker=dict(market_dispatch=lists["wind_pem", "test_track_market_dispatch", "market_dispatch"],
+                              expected_wind_power=lists["wind_pem", "test_track_market_dispatch", "expected_wind_power"],
+                              rel=1e-3, abs_power=1e-3, tracking_horizon=4, n_tracking_hour=1, pem_pmax_mw=25.0),
         cf_309_rt=df["309_WIND_1-RTCF"].values[:48].tolist(),
         da_309=df["309_DALMP"].values[:48].tolist(), rt_309=df["309_RTLMP"].values[:48].tolist(),
         wind_pmax_mw=200.0, battery_pmax_mw=25.0, battery_energy_capacity_mwh=100.0,

@@ -243,6 +243,31 @@ def test_host_nuclear_logic(monkeypatch):
     _check_nuclear(2)
 
 
+def test_oracle_and_host_wind_pem_tracker_known_answer(monkeypatch):
+    """wind + PEM tracker against the reference's known answers (tests/test_wind_PEM_double_loop.py:55-121)."""
+    g = G["wind_pem_tracker"]
+    lp = DL.wind_pem_tracker_raw(g["market_dispatch"], CF[:4], G["wind_pmax_mw"], g["pem_pmax_mw"])
+    ref_obj, x = H.solve(lp)
+    v = lp.meta["v"]
+    wind = np.array([x[v["w", t]] for t in range(4)]); pem = np.array([x[v["pe", t]] for t in range(4)])
+    assert CF[0] == pytest.approx(0.00562, rel=1e-3)                                                     # :77-78
+    assert wind == pytest.approx(g["expected_wind_power"], rel=g["rel"])                                 # :93-98
+    assert np.array([x[v["g", t]] for t in range(4)]) * 1e-3 == pytest.approx(g["market_dispatch"], abs=g["abs_power"])
+    assert pem == pytest.approx(np.array(g["expected_wind_power"]) - 1e3 * np.array(g["market_dispatch"]), rel=g["rel"])   # :112-119
+    # reduced template and host class (HiGHS stand-in for the CUDA solve)
+    monkeypatch.setattr(DLH, "_lp_solve", highs_lp_solve)
+    md = DLH.RenewableGeneratorModelData("309_WIND_1", "Carter", 0, 200)
+    m = DLH.MultiPeriodWindPEM(md, np.tile(CF, 2), wind_pmax_mw=200, pem_pmax_mw=25)
+    tr = DLH.Tracker(m, tracking_horizon=4, n_tracking_hour=1)
+    tr.track_market_dispatch(g["market_dispatch"], date="2020-01-02", hour="00:00")
+    assert tr.objective[0] == pytest.approx(ref_obj, rel=1e-9)
+    assert tr.fs.sol["pem"][0] == pytest.approx(pem, rel=1e-6, abs=1e-3)
+    assert np.all(np.abs(tr.fs.wind_waste) < 1e-3)                                                       # :99-102
+    assert tr.power_output[0] == pytest.approx(g["market_dispatch"], abs=g["abs_power"])
+    assert tr.fs._time_idx == 1 and np.allclose(tr.fs.cf[0], CF[1:5])
+    assert "Wind to PEM [MW]" in m.result_list[0].columns
+
+
 def test_backcaster_order():
     bc = DLH.Backcaster({"b": np.arange(72.0)}, {"b": np.arange(72.0)})
     f = bc.forecast_day_ahead_prices("d", 0, "b", 48, 2)
