@@ -233,8 +233,9 @@ def test_reference_shaped_api():
     assert res.annual_revenue[0] == pytest.approx(rep["annual_revenue"], rel=1e-5)
     soc, wind_gen, b2g, w2g, w2b, rev, lmps, wcap, bcap, ann, npv = PT.record_results(res, 0)
     assert len(soc) == 24 and soc[-1] == 0.0 and wcap == pytest.approx(W) and npv == pytest.approx(res.NPV[0])
-    with pytest.raises(NotImplementedError):
-        PT.wind_battery_optimize(24, dict(params, design_opt=True, extant_wind=False))
+    with pytest.raises(NotImplementedError):     # a free wind size needs one capacity-factor series for the whole batch
+        PT.wind_battery_optimize(24, dict(params, design_opt=True, extant_wind=False,
+                                          wind_resource=np.stack([cf * (1 - 0.01 * k) for k in range(16)])))
 
 
 def test_sweep_drivers_write_reference_shaped_results(tmp_path):
