@@ -56,6 +56,21 @@ def _columns(template, xm, T):
     return out
 
 
+def _result_frame(N, H, const_cols, array_cols, kwargs):
+    """The reference builds its result table row by row; here one frame per call from [N, H] arrays (rounded to 2
+    decimals like the reference), row order (simulation, horizon hour)."""
+    import pandas as pd
+    data = {k: [v] * (N * H) for k, v in const_cols.items()}
+    data["Horizon [hr]"] = np.tile(np.arange(H), N)
+    for k, a in array_cols.items():
+        data[k] = np.round(np.asarray(a, float).reshape(N * H), 2)
+    if N > 1:
+        data["Simulation"] = np.repeat(np.arange(N), H)
+    for k, v in kwargs.items():
+        data[k] = [v] * (N * H)
+    return pd.DataFrame(data)
+
+
 # ---- minimal stand-ins for idaes.apps.grid_integration.model_data (only the fields the reference's tests set)
 @dataclasses.dataclass
 class RenewableGeneratorModelData:
@@ -214,25 +229,17 @@ class MultiPeriodWindBattery:
 
     def record_results(self, b, date=None, hour=None, **kwargs):
         """Rows of the reference's result table (:272-335), one per (simulation, horizon hour)."""
-        import pandas as pd
-        rows = []
-        wind_gen = (b.sol["grid"] + b.sol["batt_in"]) * 1e-3
-        for k in range(self.N):
-            for t in range(b.horizon):
-                row = {"Generator": self.model_data.gen_name, "Date": date, "Hour": hour, "Horizon [hr]": int(t),
-                       "Total Wind Generation [MW]": round(float(wind_gen[k, t]), 2),
-                       "Total Power Output [MW]": round(float(b.P_T[k, t]), 2),
-                       "Wind Power Output [MW]": round(float(b.sol["grid"][k, t] * 1e-3), 2),
-                       "Wind Curtailment [MW]": round(float(b.wind_waste[k, 0]), 2),        # the reference reads index 0 (:309)
-                       "Battery Power Output [MW]": round(float(b.sol["batt_out"][k, t] * 1e-3), 2),
-                       "Wind Power to Battery [MW]": round(float(b.sol["batt_in"][k, t] * 1e-3), 2),
-                       "State of Charge [MWh]": round(float(b.sol["soc"][k, t] * 1e-3), 2),
-                       "Total Cost [$]": round(float(b.tot_cost[k, t]), 2)}
-                if self.N > 1:
-                    row["Simulation"] = k
-                row.update(kwargs)
-                rows.append(row)
-        self.result_list.append(pd.DataFrame(rows))
+        H = b.horizon
+        cols = {"Total Wind Generation [MW]": (b.sol["grid"] + b.sol["batt_in"]) * 1e-3,
+                "Total Power Output [MW]": b.P_T,
+                "Wind Power Output [MW]": b.sol["grid"] * 1e-3,
+                "Wind Curtailment [MW]": np.repeat(b.wind_waste[:, :1], H, axis=1),        # the reference reads index 0 (:309)
+                "Battery Power Output [MW]": b.sol["batt_out"] * 1e-3,
+                "Wind Power to Battery [MW]": b.sol["batt_in"] * 1e-3,
+                "State of Charge [MWh]": b.sol["soc"] * 1e-3,
+                "Total Cost [$]": b.tot_cost}
+        self.result_list.append(_result_frame(self.N, H, {"Generator": self.model_data.gen_name, "Date": date, "Hour": hour},
+                                              cols, kwargs))
 
     def write_results(self, path):
         import pandas as pd
@@ -305,24 +312,17 @@ class MultiPeriodWindPEM:
 
     def record_results(self, b, date=None, hour=None, **kwargs):
         """Rows of the reference's table (:265-320)."""
-        import pandas as pd
         k = TP.PEM_ELEC_TO_MOL / TP.H2_MOLS_PER_KG * 3600.0
-        rows = []
-        for n in range(self.N):
-            for t in range(b.horizon):
-                row = {"Generator": self.model_data.gen_name, "Date": date, "Hour": hour, "Horizon [hr]": int(t),
-                       "Total Wind Generation [MW]": round(float((b.sol["grid"][n, t] + b.sol["pem"][n, t]) * 1e-3), 2),
-                       "Total Power Output [MW]": round(float(b.P_T[n, t]), 2),
-                       "Wind Power Output [MW]": round(float(b.sol["grid"][n, t] * 1e-3), 2),
-                       "Wind to PEM [MW]": round(float(b.sol["pem"][n, t] * 1e-3), 2),
-                       "Wind Curtailment [MW]": round(float(b.wind_waste[n, 0]), 2),       # the reference reads index 0, in kW (:302)
-                       "Hydrogen Sales [kg]": round(float(b.sol["pem"][n, t] * k), 2),
-                       "Total Cost [$]": round(float(b.tot_cost[n, t]), 2)}
-                if self.N > 1:
-                    row["Simulation"] = n
-                row.update(kwargs)
-                rows.append(row)
-        self.result_list.append(pd.DataFrame(rows))
+        H = b.horizon
+        cols = {"Total Wind Generation [MW]": (b.sol["grid"] + b.sol["pem"]) * 1e-3,
+                "Total Power Output [MW]": b.P_T,
+                "Wind Power Output [MW]": b.sol["grid"] * 1e-3,
+                "Wind to PEM [MW]": b.sol["pem"] * 1e-3,
+                "Wind Curtailment [MW]": np.repeat(b.wind_waste[:, :1], H, axis=1),        # the reference reads index 0, in kW (:302)
+                "Hydrogen Sales [kg]": b.sol["pem"] * k,
+                "Total Cost [$]": b.tot_cost}
+        self.result_list.append(_result_frame(self.N, H, {"Generator": self.model_data.gen_name, "Date": date, "Hour": hour},
+                                              cols, kwargs))
 
     def write_results(self, path):
         import pandas as pd
@@ -380,23 +380,14 @@ class MultiPeriodNuclear:
 
     def record_results(self, blk, date=None, hour=None, **kwargs):
         """Rows of the reference's table (:281-320)."""
-        import pandas as pd
         prev = np.concatenate([blk.holdup0[:, None], blk.sol["holdup"][:, :-1]], axis=1)
-        rows = []
-        for k in range(self.N):
-            for t in range(blk.horizon):
-                row = {"Date": date, "Hour": hour, "Horizon [hr]": int(t),
-                       "Power to Grid [MW]": round(float(blk.P_T[k, t]), 2),
-                       "Power to PEM [MW]": round(float(blk.sol["pem"][k, t] * 1e-3), 2),
-                       "Initial holdup [kg]": round(float(prev[k, t] * self.MW_H2), 2),
-                       "Final holdup [kg]": round(float(blk.sol["holdup"][k, t] * self.MW_H2), 2),
-                       "Hydrogen Market [kg/hr]": round(float(blk.sol["pipeline"][k, t] * self.MW_H2 * 3600), 2),
-                       "Total Cost [$]": round(float(blk.tot_cost[k, t]), 2)}
-                if self.N > 1:
-                    row["Simulation"] = k
-                row.update(kwargs)
-                rows.append(row)
-        self.result_list.append(pd.DataFrame(rows))
+        cols = {"Power to Grid [MW]": blk.P_T,
+                "Power to PEM [MW]": blk.sol["pem"] * 1e-3,
+                "Initial holdup [kg]": prev * self.MW_H2,
+                "Final holdup [kg]": blk.sol["holdup"] * self.MW_H2,
+                "Hydrogen Market [kg/hr]": blk.sol["pipeline"] * self.MW_H2 * 3600,
+                "Total Cost [$]": blk.tot_cost}
+        self.result_list.append(_result_frame(self.N, blk.horizon, {"Date": date, "Hour": hour}, cols, kwargs))
 
     def write_results(self, path):
         import pandas as pd
