@@ -491,6 +491,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) dsp_ipm_band_kernel(const K
     if (WS && P.hybrid) band0 = (double *)(smem + P.prob_off) + (size_t)warp * P.band_doubles;
     W.dy = band0 + BW;
     W.Mb = W.dy + m + BW + BW * (BW + 1);
+#ifdef DSP_EXPERIMENT_HYBRID2
+    // round-2 experiment (tools/build_variants.py): the gather sources of the CSR product and of the assembly (dx, d) next
+    // to the band in shared memory; P.band_doubles then includes 2 n
+    if (WS && P.hybrid == 2) { W.dx = band0 + (P.band_doubles - 2 * n); W.d = W.dx + n; }
+#endif
     for (;;) {
         unsigned long long t = 0;
         if (lane == 0) t = atomicAdd(P.ticket, 1ULL);
@@ -854,7 +859,13 @@ void dsp_lp_template_destroy(dsp_template *T) {
 struct BandGeom { long long warps; int hot_in_smem; size_t off; bool ws; int hybrid; };
 
 BandGeom band_geometry(const dsp_template *T, const KParams &K) {
-    const size_t prob_bytes = (size_t)K.prob_doubles * 8, band_bytes = (size_t)K.band_doubles * 8;
+    const size_t prob_bytes = (size_t)K.prob_doubles * 8;
+    size_t band_bytes = (size_t)K.band_doubles * 8;
+#ifdef DSP_EXPERIMENT_HYBRID2
+    const char *h2 = getenv("DSP_BAND_MODE");
+    const bool hybrid2 = h2 && !strcmp(h2, "hybrid2");
+    if (hybrid2) band_bytes += (size_t)2 * K.n * 8;
+#endif
     const size_t budget = (size_t)T->smem_optin;
     BandGeom g{0, 1, 16 + (size_t)K.hot_bytes, false, 0};
     long long smem_warps = budget > g.off ? (long long)((budget - g.off) / prob_bytes) : 0;
@@ -868,6 +879,9 @@ BandGeom band_geometry(const dsp_template *T, const KParams &K) {
     if (const char *e = getenv("DSP_BAND_MODE")) {            // experiment switch
         if (!strcmp(e, "ws")) mode = M_WS;
         else if (!strcmp(e, "hybrid") && hybrid_warps >= 1) mode = M_HYBRID;
+#ifdef DSP_EXPERIMENT_HYBRID2
+        else if (hybrid2 && hybrid_warps >= 1) mode = M_HYBRID;
+#endif
         else if (!strcmp(e, "smem") && smem_warps >= 1) mode = M_SMEM;
     }
     if (mode == M_SMEM) {
@@ -875,6 +889,9 @@ BandGeom band_geometry(const dsp_template *T, const KParams &K) {
     } else {
         g.ws = true; g.hot_in_smem = 0; g.off = 16;
         g.hybrid = mode == M_HYBRID;
+#ifdef DSP_EXPERIMENT_HYBRID2
+        if (g.hybrid && hybrid2) g.hybrid = 2;
+#endif
         g.warps = g.hybrid ? hybrid_warps : kMaxWarps;
         while (g.warps > 1 && (size_t)T->sm_count * (size_t)g.warps * prob_bytes > ((size_t)48 << 30)) g.warps /= 2;
     }
@@ -918,8 +935,11 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         return DSP_E_ARG;
     }
     const size_t prob_bytes = (size_t)K.prob_doubles * 8;
-    const size_t band_bytes = (size_t)K.band_doubles * 8;
     const BandGeom geom = band_geometry(T, K);
+#ifdef DSP_EXPERIMENT_HYBRID2
+    if (geom.hybrid == 2) K.band_doubles += 2 * K.n;
+#endif
+    const size_t band_bytes = (size_t)K.band_doubles * 8;
     long long warps = geom.warps;
     const int hot_in_smem = geom.hot_in_smem, hybrid = geom.hybrid;
     const size_t off = geom.off;

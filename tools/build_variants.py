@@ -3,13 +3,8 @@ import subprocess, sys, concurrent.futures as cf
 sys.path.insert(0, ".")
 from dispatches_b200.csrc import build as B
 VARIANTS = {
-    "a0_base_ku16": [],
-    "a1_base_ku1": ["-DDSP_STAGE_KU=1"],
-    "a2_base_ku2": ["-DDSP_STAGE_KU=2"],
-    "a3_defer_ku1": ["-DDSP_DEFER_RCP", "-DDSP_STAGE_KU=1"],
-    "a4_defer_ku2": ["-DDSP_DEFER_RCP", "-DDSP_STAGE_KU=2"],
-    "a5_generic_base": ["-DDSP_STAGE_GENERIC_ONLY"],
-    "a6_generic_defer": ["-DDSP_STAGE_GENERIC_ONLY", "-DDSP_DEFER_RCP"],
+    "r2_base": [],
+    "r2_hybrid2": ["-DDSP_EXPERIMENT_HYBRID2"],      # run with DSP_BAND_MODE=hybrid2 (tools/gpu_band_modes.py)
 }
 out = B.ROOT / "build" / "variants"
 out.mkdir(parents=True, exist_ok=True)
