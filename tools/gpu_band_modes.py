@@ -22,11 +22,13 @@ l2, cf2, W2, P2 = SC.c2(10000)
 cases["wind_battery_pem_T24"] = (TP.wind_battery_pem(24), torch.tensor(np.concatenate([l2, np.full((10000, 1), 2.5)], axis=1), device=dev),
                                  torch.tensor(TP.wind_battery_rparams(24, cf2, W2, 150.0, pem_mw=200.0)[0], device=dev))
 cases["C3_nuclear_T48"] = (TP.nuclear(48), torch.tensor(SC.c3(5000), device=dev), None)
+MODES = [a.split("=")[1] for a in sys.argv if a.startswith("--modes=")]
+MODES = MODES[0].split(",") if MODES else ["smem", "hybrid", "ws"]      # hybrid2 needs a -DDSP_EXPERIMENT_HYBRID2 build (DSP_LP_LIB)
 out = {}
 for name, (t, cp, rp) in cases.items():
     sol = S.BatchLPSolver(t)
     ref = None
-    for mode in ("smem", "hybrid", "ws"):
+    for mode in MODES:
         os.environ["DSP_BAND_MODE"] = mode
         o = sol.solve(cp, rp); torch.cuda.synchronize()
         ts = []
