@@ -5,6 +5,9 @@ from dispatches_b200.csrc import build as B
 VARIANTS = {
     "r2_base": [],
     "r2_hybrid2": ["-DDSP_EXPERIMENT_HYBRID2"],      # run with DSP_BAND_MODE=hybrid2 (tools/gpu_band_modes.py)
+    "r2_park_168": ["-DDSP_STAGE_PARK"],             # parked temporaries at the current 168-register / 12-warp point
+    "r2_park_128": ["-DDSP_STAGE_PARK", "-DDSP_STAGE_MINB=4"],     # 128 registers / 16 warps per SM
+    "r2_nopark_128": ["-DDSP_STAGE_MINB=4"],
 }
 out = B.ROOT / "build" / "variants"
 out.mkdir(parents=True, exist_ok=True)
