@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(32 * DSP_STAGE_WPB, DSP_STAGE_MINB) dsp_ipm_st
         for (int attempt = 0; attempt < 2; ++attempt) {
             const double sf = attempt ? 0.99 : P.step_frac, rg = attempt ? 10.0 * P.reg : P.reg;
 #ifdef DSP_STAGE_PARK
-            __shared__ double park_all[DSP_STAGE_WPB][22 * 32];
+            __shared__ double park_all[DSP_STAGE_WPB][(DSP_STAGE_PARK >= 2 ? 40 : 22) * 32];
             const int r = stagewb::solve_one(S, cp, rp, kconst, (long long)t, P.tol, P.feas_tol, sf, rg, P.max_iter, O, lane, it0,
                                              park_all[threadIdx.x >> 5] + lane);
 #else

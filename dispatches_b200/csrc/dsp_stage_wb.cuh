@@ -76,10 +76,18 @@ __device__ __forceinline__ double wsum(double v) {
 #define PARK_ST(k, v) park[(k) * 32] = (v)
 #define PARK_LD(k, v) park[(k) * 32]
 #define PARK_PARAM , double *park
+#if DSP_STAGE_PARK >= 2      // also the right-hand-side pieces that wait for the solves and the predictor's second-order products
+#define PARK2_ST(k, v) park[(k) * 32] = (v)
+#define PARK2_LD(k, v) park[(k) * 32]
+#endif
 #else
 #define PARK_ST(k, v) ((void)0)
 #define PARK_LD(k, v) (v)
 #define PARK_PARAM
+#endif
+#ifndef PARK2_ST
+#define PARK2_ST(k, v) ((void)0)
+#define PARK2_LD(k, v) (v)
 #endif
 
 struct Sym2 { double a, b, c; };            // [[a, b], [b, c]]
@@ -290,9 +298,9 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
             hg = PARK_LD(4, rdg) + zg; hi = PARK_LD(5, rdi) + zi; ho = PARK_LD(6, rdo) + zo; hs = PARK_LD(7, rds) + zs; he = PARK_LD(8, rde) + ze; hp = PARK_LD(9, rdp) + zp; hq = PARK_LD(10, rdq) + zq;
             double asi = -wi * PARK_LD(11, rui), aso = -wo * PARK_LD(12, ruo);
             if (corr) {
-                hg -= (smu - cg) * rxg; hi -= (smu - ci) * rxi; ho -= (smu - co) * rxo; hs -= (smu - cs) * rxs;
-                he -= (smu - ce) * rxe; hp -= (smu - cpp) * rxp; hq -= (smu - cq) * rxq;
-                asi += smu - csi; aso += smu - cso;
+                hg -= (smu - PARK2_LD(31, cg)) * rxg; hi -= (smu - PARK2_LD(32, ci)) * rxi; ho -= (smu - PARK2_LD(33, co)) * rxo; hs -= (smu - PARK2_LD(34, cs)) * rxs;
+                he -= (smu - PARK2_LD(35, ce)) * rxe; hp -= (smu - PARK2_LD(36, cpp)) * rxp; hq -= (smu - PARK2_LD(37, cq)) * rxq;
+                asi += smu - PARK2_LD(38, csi); aso += smu - PARK2_LD(39, cso);
             }
             hi += asi * rsi - wi; ho += aso * rso - wo;
             if (!has_s) hs = 0.0;
@@ -305,20 +313,21 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
             f1 = PARK_LD(0, rp1) + ph1 - up1(ph1, lane) - a * psi + binv * doh;
             f2 = PARK_LD(1, rp2) + ph2 - up1(ph2, lane) - hf * psi - hf * doh;
             if (!act) { f1 = 0.0; f2 = 0.0; }
+            PARK2_ST(22, hg); PARK2_ST(23, hi); PARK2_ST(24, ho); PARK2_ST(25, hs); PARK2_ST(26, he); PARK2_ST(27, hp); PARK2_ST(28, hq); PARK2_ST(29, w3); PARK2_ST(30, w4);
         };
         auto recover = [&](double u1, double u2) {
             dy1 = u1; dy2 = u2;
-            const double e1 = dy1 - down1(dy1, lane) - hs, e2 = dy2 - down1(dy2, lane) - he;
+            const double e1 = dy1 - down1(dy1, lane) - PARK2_LD(25, hs), e2 = dy2 - down1(dy2, lane) - PARK2_LD(26, he);
             const double v = a * dy1 + hf * dy2;
-            dxs = has_s ? s11 * e1 - s12 * e2 + dsk * w3 : 0.0;
-            dxe = s22 * e2 - s12 * e1 + dek * w3;
-            dxi = -tau * (v + hi) + dii * w4;
-            dxo = dO * (binv * dy1 - hf * dy2 - ho);
-            dxg = dg * iot * (PARK_LD(3, rp4) + di * (hi - hg + v) + dq * (hq - hg));
-            dy3 = kap * (w3 - ds * e1 - dl * de * e2);
-            dy4 = iot * (w4 + di * (hi + v));
-            dxp = dp * (dy3 - hp);
-            dxq = dq * (dy4 - hq);
+            dxs = has_s ? s11 * e1 - s12 * e2 + dsk * PARK2_LD(29, w3) : 0.0;
+            dxe = s22 * e2 - s12 * e1 + dek * PARK2_LD(29, w3);
+            dxi = -tau * (v + PARK2_LD(23, hi)) + dii * PARK2_LD(30, w4);
+            dxo = dO * (binv * dy1 - hf * dy2 - PARK2_LD(24, ho));
+            dxg = dg * iot * (PARK_LD(3, rp4) + di * (PARK2_LD(23, hi) - PARK2_LD(22, hg) + v) + dq * (PARK2_LD(28, hq) - PARK2_LD(22, hg)));
+            dy3 = kap * (PARK2_LD(29, w3) - ds * e1 - dl * de * e2);
+            dy4 = iot * (PARK2_LD(30, w4) + di * (PARK2_LD(23, hi) + v));
+            dxp = dp * (dy3 - PARK2_LD(27, hp));
+            dxq = dq * (dy4 - PARK2_LD(28, hq));
         };
         // ---- twisted block LDL'; the forward elimination of the PREDICTOR right-hand side rides along in the same
         // ---- sweep (its shuffles and FMAs fill the latency shadow of the 2x2 inversions)
@@ -394,6 +403,7 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
         mua = wsum(mua) / ntot;
         cg = dxg * dzg; ci = dxi * dzi; co = dxo * dzo; cs = dxs * dzs; ce = dxe * dze; cpp = dxp * dzp; cq = dxq * dzq;
         csi = dsi * dwi; cso = dso * dwo;
+        PARK2_ST(31, cg); PARK2_ST(32, ci); PARK2_ST(33, co); PARK2_ST(34, cs); PARK2_ST(35, ce); PARK2_ST(36, cpp); PARK2_ST(37, cq); PARK2_ST(38, csi); PARK2_ST(39, cso);
         const double sg = mua / mu;
         smu = sg * sg * sg * mu;
         PH(13);
@@ -402,12 +412,12 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
         tw_solve(F, g1, g2, T, lane);
         PH(14);
         recover(g1, g2);
-        dzg = (smu - cg) * rxg - zg - zg * dxg * rxg; dzi = (smu - ci) * rxi - zi - zi * dxi * rxi;
-        dzo = (smu - co) * rxo - zo - zo * dxo * rxo; dzs = has_s ? (smu - cs) * rxs - zs - zs * dxs * rxs : 0.0;
-        dze = (smu - ce) * rxe - ze - ze * dxe * rxe; dzp = (smu - cpp) * rxp - zp - zp * dxp * rxp;
-        dzq = (smu - cq) * rxq - zq - zq * dxq * rxq;
+        dzg = (smu - PARK2_LD(31, cg)) * rxg - zg - zg * dxg * rxg; dzi = (smu - PARK2_LD(32, ci)) * rxi - zi - zi * dxi * rxi;
+        dzo = (smu - PARK2_LD(33, co)) * rxo - zo - zo * dxo * rxo; dzs = has_s ? (smu - PARK2_LD(34, cs)) * rxs - zs - zs * dxs * rxs : 0.0;
+        dze = (smu - PARK2_LD(35, ce)) * rxe - ze - ze * dxe * rxe; dzp = (smu - PARK2_LD(36, cpp)) * rxp - zp - zp * dxp * rxp;
+        dzq = (smu - PARK2_LD(37, cq)) * rxq - zq - zq * dxq * rxq;
         dsi = PARK_LD(11, rui) - dxi; dso = PARK_LD(12, ruo) - dxo;
-        dwi = (smu - csi) * rsi - wi - wi * dsi * rsi; dwo = (smu - cso) * rso - wo - wo * dso * rso;
+        dwi = (smu - PARK2_LD(38, csi)) * rsi - wi - wi * dsi * rsi; dwo = (smu - PARK2_LD(39, cso)) * rso - wo - wo * dso * rso;
         ip = 0.0; id = 0.0;
         if (act) {
             ip = dmax(dmax(dmax(-dxg * rxg, -dxi * rxi), dmax(-dxo * rxo, -dxs * rxs)), dmax(dmax(-dxe * rxe, -dxp * rxp), -dxq * rxq));

@@ -5,8 +5,10 @@ from dispatches_b200.csrc import build as B
 VARIANTS = {
     "r2_base": [],
     "r2_hybrid2": ["-DDSP_EXPERIMENT_HYBRID2"],      # run with DSP_BAND_MODE=hybrid2 (tools/gpu_band_modes.py)
-    "r2_park_168": ["-DDSP_STAGE_PARK"],             # parked temporaries at the current 168-register / 12-warp point
-    "r2_park_128": ["-DDSP_STAGE_PARK", "-DDSP_STAGE_MINB=4"],     # 128 registers / 16 warps per SM
+    "r2_park_168": ["-DDSP_STAGE_PARK=1"],             # parked temporaries at the current 168-register / 12-warp point
+    "r2_park_128": ["-DDSP_STAGE_PARK=1", "-DDSP_STAGE_MINB=4"],     # 128 registers / 16 warps per SM
+    "r2_park2_128": ["-DDSP_STAGE_PARK=2", "-DDSP_STAGE_MINB=4"],    # 40 parked doubles per lane
+    "r2_park2_112": ["-DDSP_STAGE_PARK=2", "-DDSP_STAGE_WPB=2", "-DDSP_STAGE_MINB=9"],   # 112 registers / 18 warps per SM
     "r2_nopark_128": ["-DDSP_STAGE_MINB=4"],
 }
 out = B.ROOT / "build" / "variants"
