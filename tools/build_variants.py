@@ -8,7 +8,8 @@ VARIANTS = {
     "r2_park_168": ["-DDSP_STAGE_PARK=1"],             # parked temporaries at the current 168-register / 12-warp point
     "r2_park_128": ["-DDSP_STAGE_PARK=1", "-DDSP_STAGE_MINB=4"],     # 128 registers / 16 warps per SM
     "r2_park2_128": ["-DDSP_STAGE_PARK=2", "-DDSP_STAGE_MINB=4"],    # 40 parked doubles per lane
-    "r2_park2_112": ["-DDSP_STAGE_PARK=2", "-DDSP_STAGE_WPB=2", "-DDSP_STAGE_MINB=9"],   # 112 registers / 18 warps per SM
+    "r2_park2_96": ["-DDSP_STAGE_PARK=2", "-DDSP_STAGE_MINB=5"],     # 96 registers / 20 warps per SM (5 CTAs x 4 warps, 40 KB smem each)
+    "r2_park2_112": ["-DDSP_STAGE_PARK=2", "-DDSP_STAGE_WPB=2", "-DDSP_STAGE_MINB=9"],   # ptxas picks 96 registers / 18 warps per SM
     "r2_nopark_128": ["-DDSP_STAGE_MINB=4"],
 }
 out = B.ROOT / "build" / "variants"
