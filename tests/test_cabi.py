@@ -40,7 +40,7 @@ def test_sass_is_sm100a_with_tma_staging():
 
 def test_no_cpu_fallback_in_product():
     """The product package never imports the oracle and the solver refuses non-CUDA tensors."""
-    for p in (ROOT / "dispatches_b200").rglob("*.py"):
+    for p in list((ROOT / "dispatches_b200").rglob("*.py")) + list((ROOT / "tools").rglob("*.py")):
         src = p.read_text()
         assert "import oracle" not in src and "from oracle" not in src, p
     import numpy as np
