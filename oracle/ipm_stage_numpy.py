@@ -18,7 +18,7 @@ from __future__ import annotations
 import numpy as np
 
 OPTIMAL, MAXITER, NUMERR = 0, 1, 2
-INV = "ldl"
+INV = "ldl"         # "adj" (adjugate / determinant) | "defer" (the kernel's deferred-reciprocal elimination step)
 MODE = "twisted"     # "pcr" | "refine" (one step of iterative refinement) | "dense" (LAPACK, for diagnosis)
 
 
@@ -138,10 +138,21 @@ class PCR:
         if not hasattr(self, "_tw"):
             Dh = D.copy(); G = np.zeros_like(D); G2 = np.zeros((N, 2, 2))
             mm = lambda A, B: np.einsum("nij,njk->nik", A, B)
+            def step(C, R, Ct, Dt):
+                """G = C R^-1, Dh = D - G C'.  INV == "defer" mirrors the kernel's elimination step: the neighbour's block R
+                itself is passed on, X = C adj(R) and X C' are formed while 1/det(R) is in flight, one FMA finishes."""
+                if INV != "defer":
+                    Gt = mm(C, _inv2(R))
+                    return Gt, Dt - mm(Gt, Ct)
+                rd = (1.0 / (R[:, 0, 0] * R[:, 1, 1] - R[:, 0, 1] * R[:, 1, 0]))[:, None, None]
+                adj = np.empty_like(R)
+                adj[:, 0, 0] = R[:, 1, 1]; adj[:, 1, 1] = R[:, 0, 0]; adj[:, 0, 1] = -R[:, 0, 1]; adj[:, 1, 0] = -R[:, 1, 0]
+                X = mm(C, adj)
+                return X * rd, Dt - mm(X, Ct) * rd
             for t in range(1, r):                       # chain A, downwards
-                G[:, t] = mm(L[:, t], _inv2(Dh[:, t - 1])); Dh[:, t] = D[:, t] - mm(G[:, t], U[:, t - 1])
+                G[:, t], Dh[:, t] = step(L[:, t], Dh[:, t - 1], U[:, t - 1], D[:, t])
             for t in range(T - 2, r, -1):               # chain B, upwards
-                G[:, t] = mm(U[:, t], _inv2(Dh[:, t + 1])); Dh[:, t] = D[:, t] - mm(G[:, t], L[:, t + 1])
+                G[:, t], Dh[:, t] = step(U[:, t], Dh[:, t + 1], L[:, t + 1], D[:, t])
             if r >= 1:
                 G[:, r] = mm(L[:, r], _inv2(Dh[:, r - 1])); Dh[:, r] = D[:, r] - mm(G[:, r], U[:, r - 1])
             if r + 1 <= T - 1:

@@ -65,3 +65,22 @@ def test_stage_mirror_matches_generic_mirror_and_highs():
         ref = H.solve(L.wind_battery_raw(lmp5[i], cf5[i], w5[i], b5[i]))[0]
         ki = t.instantiate(lmp5[i], TP.wind_battery_rparams(24, cf5[i], w5[i], b5[i])[0])[3]
         assert abs(s5["obj_lp"][i] + ki - ref) / max(1.0, abs(ref)) < TOL_OBJ
+
+
+def test_stage_mirror_deferred_reciprocal_step(monkeypatch):
+    """INV="defer" restates the kernel's elimination step (the neighbour's block is passed on, C adj(R) C' is formed while
+    1/det(R) is in flight): same iteration counts and objectives as the LDL' inverse on the C2 sample and the C5 slice."""
+    from oracle import ipm_stage_numpy as ST
+    t = TP.wind_battery(24)
+    st = t.meta["stage_wb"]
+    consts = {k: st[k] for k in ("a", "binv", "half", "delta", "dur", "k_rev")}
+    lmp, cf, W, P = SC.c2(120)
+    lmp5, cf5, w5, b5 = SC.c5(4, 4, 40)
+    ref = ST.solve_batch(lmp, W * 1e3 * cf, P * 1e3, consts)
+    ref5 = ST.solve_batch(lmp5, (w5 * 1e3)[:, None] * cf5, b5 * 1e3, consts)
+    monkeypatch.setattr(ST, "INV", "defer")
+    s = ST.solve_batch(lmp, W * 1e3 * cf, P * 1e3, consts)
+    s5 = ST.solve_batch(lmp5, (w5 * 1e3)[:, None] * cf5, b5 * 1e3, consts)
+    assert (s["status"] == 0).all() and (s5["status"] == 0).all()
+    assert (s["iters"] == ref["iters"]).mean() > 0.95 and (s5["iters"] == ref5["iters"]).mean() > 0.9
+    assert (np.abs(s["obj_lp"] - ref["obj_lp"]) / np.maximum(1e-3, np.abs(ref["obj_lp"]))).max() < 1e-6
