@@ -11,6 +11,7 @@ VARIANTS = {
     "r2_park2_96": ["-DDSP_STAGE_PARK=2", "-DDSP_STAGE_MINB=5"],     # 96 registers / 20 warps per SM (5 CTAs x 4 warps, 40 KB smem each)
     "r2_park2_112": ["-DDSP_STAGE_PARK=2", "-DDSP_STAGE_WPB=2", "-DDSP_STAGE_MINB=9"],   # ptxas picks 96 registers / 18 warps per SM
     "r2_nopark_128": ["-DDSP_STAGE_MINB=4"],
+    "r2_start1": ["-DDSP_STAGE_START=1"],            # primal-feasible start; time it with BatchLPSolver(step_frac=0.99995) too
     # per-phase cycle counters (tools/gpu_phases.py with DSP_LP_LIB): where do 16 warps per SM lose what they gain?
     "r2_phases_base": ["-DDSP_PHASES"],
     "r2_phases_park_128": ["-DDSP_PHASES", "-DDSP_STAGE_PARK=1", "-DDSP_STAGE_MINB=4"],
