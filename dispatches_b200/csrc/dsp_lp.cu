@@ -297,6 +297,7 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
     const double beta_c = cmax > 0.0 ? cmax : 1.0;
     // ---- scale, start point, zero the paddings
     double bsmax = 0.0;
+    bool bad_u = false;             // a negative upper bound (Umap / rparams): the LP is infeasible, not "u = 1e-10"
     for (int i = lane; i < m; i += 32) {
         const double v = W.b[i] / beta_b;
         W.b[i] = v;
@@ -307,6 +308,7 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
         W.c[j] = W.c[j] / beta_c;
         double xj = 1.0;
         if (j < nb) {
+            bad_u |= W.u[j] < -1e-9 * beta_b;
             const double uj = dmaxd(W.u[j] / beta_b, 1e-10);
             W.u[j] = uj;
             xj = fmin(1.0, 0.5 * uj);
@@ -322,6 +324,12 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
     const double nrm_b = 1.0 + bsmax, nrm_c = 1.0 + (cmax > 0.0 ? 1.0 : 0.0);
     const double ntot = (double)(n + nb);
     __syncwarp();
+    if (__any_sync(0xffffffffu, bad_u)) {
+        if (lane == 0) { P.obj[p] = __longlong_as_double(0x7ff8000000000000LL); P.status[p] = DSP_INFEASIBLE; P.iters[p] = it0; }
+        *status_out = DSP_OPTIMAL;          // no second attempt
+        *iters_out = it0;
+        return;
+    }
 
     int status = DSP_MAX_ITER, it = 0;
     double pobj = 0.0;
@@ -587,7 +595,10 @@ int upload(const std::vector<T> &h, T **d) {
     *d = nullptr;
     size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
     CK(cudaMalloc((void **)d, bytes));
-    if (!h.empty()) CK(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (!h.empty()) {
+        cudaError_t e_ = cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+        if (e_ != cudaSuccess) { cudaFree(*d); *d = nullptr; g_err = std::string("cudaMemcpy: ") + cudaGetErrorString(e_); return DSP_E_CUDA; }
+    }
     return 0;
 }
 
@@ -617,6 +628,8 @@ struct dsp_template {
 };
 
 extern "C" {
+
+static void free_staging(dsp_template *T);
 
 const char *dsp_lp_version(void) { return DSP_VERSION; }
 
@@ -736,6 +749,10 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
         memcpy(pi, D->asm_col, (size_t)nasm * 4);
     }
     dsp_template *T = new dsp_template();
+    struct Guard {      // every error return below releases the handle and its device allocations
+        dsp_template *t;
+        ~Guard() { if (t) dsp_lp_template_destroy(t); }
+    } guard{T};
     memset(&T->kp, 0, sizeof(KParams));
     T->cap_N = 0; T->cap_x = T->cap_y = false; T->cap_rp_rows = 0;
     T->has_stage = false; T->stage_blocks_per_sm = 0; T->ws = nullptr; T->ws_bytes = 0;
@@ -814,6 +831,7 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaStreamCreateWithFlags(&T->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&T->stream2, cudaStreamNonBlocking));
+    guard.t = nullptr;
     *out = T;
     return 0;
 }
@@ -846,10 +864,7 @@ void dsp_lp_template_destroy(dsp_template *T) {
     if (!T) return;
     for (void *p : T->dev_allocs) cudaFree(p);
     cudaFree(T->ws);
-    cudaFree(T->d_cp); cudaFree(T->d_rp); cudaFree(T->d_obj); cudaFree(T->d_x); cudaFree(T->d_y);
-    cudaFree(T->d_status); cudaFree(T->d_iters);
-    cudaFreeHost(T->h_cp); cudaFreeHost(T->h_rp); cudaFreeHost(T->h_obj); cudaFreeHost(T->h_x); cudaFreeHost(T->h_y);
-    cudaFreeHost(T->h_status); cudaFreeHost(T->h_iters);
+    free_staging(T);
     if (T->stream) cudaStreamDestroy(T->stream);
     if (T->stream2) cudaStreamDestroy(T->stream2);
     delete T;
@@ -1012,25 +1027,49 @@ int dsp_lp_solve_batch(const dsp_template *T, int64_t N, const double *cparams, 
                         T ? T->ticket : nullptr);
 }
 
-static int ensure_capacity(dsp_template *T, int64_t N, int64_t rp_rows, bool want_x, bool want_y) {
+static void free_staging(dsp_template *T) {
+    cudaFree(T->d_cp); cudaFree(T->d_rp); cudaFree(T->d_obj); cudaFree(T->d_x); cudaFree(T->d_y);
+    cudaFree(T->d_status); cudaFree(T->d_iters);
+    cudaFreeHost(T->h_cp); cudaFreeHost(T->h_rp); cudaFreeHost(T->h_obj); cudaFreeHost(T->h_x); cudaFreeHost(T->h_y);
+    cudaFreeHost(T->h_status); cudaFreeHost(T->h_iters);
+    T->d_cp = T->d_rp = T->d_obj = T->d_x = T->d_y = nullptr; T->d_status = T->d_iters = nullptr;
+    T->h_cp = T->h_rp = T->h_obj = T->h_x = T->h_y = nullptr; T->h_status = T->h_iters = nullptr;
+    T->cap_N = 0; T->cap_rp_rows = 0; T->cap_x = T->cap_y = false;
+}
+
+// Grows the device buffers (and, unless the caller's buffers are page-locked, the pinned staging buffers) of the host call.
+// On any allocation failure everything is released and the capacities are reset to 0, so a later call starts clean.
+static int ensure_capacity(dsp_template *T, int64_t N, int64_t rp_rows, bool want_x, bool want_y, bool stage_in, bool stage_out) {
     const KParams &K = T->kp;
-    if (N > T->cap_N || rp_rows > T->cap_rp_rows || (want_x && !T->cap_x) || (want_y && !T->cap_y)) {
-        int64_t cap = std::max<int64_t>(N, T->cap_N);
-        int64_t rcap = std::max<int64_t>(rp_rows, T->cap_rp_rows);
-        bool cx = want_x || T->cap_x, cy = want_y || T->cap_y;
-        cudaFree(T->d_cp); cudaFree(T->d_rp); cudaFree(T->d_obj); cudaFree(T->d_x); cudaFree(T->d_y);
-        cudaFree(T->d_status); cudaFree(T->d_iters);
-        cudaFreeHost(T->h_cp); cudaFreeHost(T->h_rp); cudaFreeHost(T->h_obj); cudaFreeHost(T->h_x); cudaFreeHost(T->h_y);
-        cudaFreeHost(T->h_status); cudaFreeHost(T->h_iters);
-        T->d_x = T->d_y = T->h_x = T->h_y = nullptr;
-        size_t ncp = (size_t)std::max<int64_t>(1, cap * K.Pc), nrp = (size_t)std::max<int64_t>(1, rcap * K.Pr);
-        CK(cudaMalloc((void **)&T->d_cp, ncp * 8)); CK(cudaMallocHost((void **)&T->h_cp, ncp * 8));
-        CK(cudaMalloc((void **)&T->d_rp, nrp * 8)); CK(cudaMallocHost((void **)&T->h_rp, nrp * 8));
-        CK(cudaMalloc((void **)&T->d_obj, cap * 8)); CK(cudaMallocHost((void **)&T->h_obj, cap * 8));
-        CK(cudaMalloc((void **)&T->d_status, cap * 4)); CK(cudaMallocHost((void **)&T->h_status, cap * 4));
-        CK(cudaMalloc((void **)&T->d_iters, cap * 4)); CK(cudaMallocHost((void **)&T->h_iters, cap * 4));
-        if (cx) { CK(cudaMalloc((void **)&T->d_x, (size_t)cap * K.n * 8)); CK(cudaMallocHost((void **)&T->h_x, (size_t)cap * K.n * 8)); }
-        if (cy) { CK(cudaMalloc((void **)&T->d_y, (size_t)cap * K.m * 8)); CK(cudaMallocHost((void **)&T->h_y, (size_t)cap * K.m * 8)); }
+    const bool need_hin = stage_in && !T->h_cp, need_hout = stage_out && (!T->h_obj || (want_x && !T->h_x) || (want_y && !T->h_y));
+    if (N > T->cap_N || rp_rows > T->cap_rp_rows || (want_x && !T->cap_x) || (want_y && !T->cap_y) || need_hin || need_hout) {
+        const int64_t cap = std::max<int64_t>(N, T->cap_N);
+        const int64_t rcap = std::max<int64_t>(rp_rows, T->cap_rp_rows);
+        const bool cx = want_x || T->cap_x, cy = want_y || T->cap_y;
+        const bool hin = stage_in || T->h_cp, hout = stage_out || T->h_obj;
+        free_staging(T);
+        const size_t ncp = (size_t)std::max<int64_t>(1, cap * K.Pc), nrp = (size_t)std::max<int64_t>(1, rcap * K.Pr);
+        cudaError_t e = cudaSuccess;
+        auto dev = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+        auto host = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMallocHost(p, bytes); };
+        dev((void **)&T->d_cp, ncp * 8); dev((void **)&T->d_rp, nrp * 8);
+        dev((void **)&T->d_obj, cap * 8); dev((void **)&T->d_status, cap * 4); dev((void **)&T->d_iters, cap * 4);
+        if (cx) dev((void **)&T->d_x, (size_t)cap * K.n * 8);
+        if (cy) dev((void **)&T->d_y, (size_t)cap * K.m * 8);
+        // the small shared-rparams row is always staged through h_rp
+        host((void **)&T->h_rp, (hin ? nrp : (size_t)std::max(1, K.Pr)) * 8);
+        if (hin) host((void **)&T->h_cp, ncp * 8);
+        if (hout) {
+            host((void **)&T->h_obj, cap * 8); host((void **)&T->h_status, cap * 4); host((void **)&T->h_iters, cap * 4);
+            if (cx) host((void **)&T->h_x, (size_t)cap * K.n * 8);
+            if (cy) host((void **)&T->h_y, (size_t)cap * K.m * 8);
+        }
+        if (e != cudaSuccess) {
+            free_staging(T);
+            cudaGetLastError();
+            g_err = std::string("dsp_lp_solve_batch_host: buffer allocation failed: ") + cudaGetErrorString(e);
+            return DSP_E_CUDA;
+        }
         T->cap_N = cap; T->cap_rp_rows = rcap; T->cap_x = cx; T->cap_y = cy;
     }
     return 0;
@@ -1043,11 +1082,14 @@ int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, c
     if (N == 0) return 0;
     const KParams &K = T->kp;
     const int64_t rp_rows = (rparams_stride == 0) ? 1 : N;
-    int rc = ensure_capacity(T, N, rp_rows, x != nullptr, y != nullptr);
-    if (rc) return rc;
+    if (!obj || !status || !iters || (K.Pc > 0 && !cparams) || (K.Pr > 0 && !rparams)) {
+        g_err = "dsp_lp_solve_batch_host: bad arguments";
+        return DSP_E_ARG;
+    }
+    if (K.Pr > 0 && rparams_stride != 0 && rparams_stride < K.Pr) { g_err = "dsp_lp_solve_batch_host: rparams_stride < Pr"; return DSP_E_ARG; }
     // chunked pipeline over two streams: the pinned-staging memcpy + H2D of chunk k+1 and the D2H of chunk k-1 overlap
     // the kernel of chunk k.  Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / a pinned
-    // torch tensor) are used directly, without the staging copy.
+    // torch tensor) are used directly, without the staging copy (and without allocating staging buffers at all).
     auto pinned = [](const void *p) {
         if (!p) return false;
         cudaPointerAttributes at;
@@ -1056,6 +1098,8 @@ int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, c
     };
     const bool in_pinned = pinned(cparams) && (K.Pr == 0 || pinned(rparams)) && (rparams_stride == 0 || rparams_stride == K.Pr);
     const bool out_pinned = pinned(obj) && pinned(status) && pinned(iters) && (!x || pinned(x)) && (!y || pinned(y));
+    int rc = ensure_capacity(T, N, rp_rows, x != nullptr, y != nullptr, !in_pinned, !out_pinned);
+    if (rc) return rc;
     cudaStream_t sts[2] = {T->stream, T->stream2};
     int64_t dstride = 0;
     const bool shared_rp = (K.Pr > 0 && rparams_stride == 0);

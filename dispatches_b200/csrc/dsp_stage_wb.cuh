@@ -3,7 +3,8 @@
 // Hot path of BASELINE configs C1/C2/C5: wind_battery_optimize with design_opt=False
 // (wind_battery_LMP.py:172-267) in the reduced form of dispatches_b200/templates.py::wind_battery.
 //
-// Mapping: ONE WARP PER LP, ONE LANE PER PERIOD, EVERYTHING IN REGISTERS (no shared memory, no local memory):
+// Mapping: ONE WARP PER LP, ONE LANE PER PERIOD, STATE IN REGISTERS (no shared memory; ptxas spills ~0.4 KB per thread
+// to local memory at the 168-register cap -- ncu r1: 9.4 M LDL + 7.7 M STL per 10 000-LP launch):
 //   lane t holds the period's 7 columns  g (grid), i (charge), o (discharge), s (state of charge), e (throughput),
 //   p (slack of the SoC bound), q (slack of the wind balance), their duals, the 4 row duals and the Newton data.
 //   Neighbouring periods talk through warp shuffles (s[t-1], e[t-1], y1[t+1], y2[t+1]).
@@ -184,6 +185,10 @@ __device__ int solve_one(const StageParams &S, const double *cp, const double *r
     const double lam = act ? cp[lane] : 0.0;
     const double wcf = act ? rpar[S.wcf_off + lane] : 0.0;
     const double P = rpar[S.p_off];
+    if (P < 0.0) {                  // negative battery power bound: infeasible (not silently clamped)
+        if (lane == 0) { O.obj[p] = __longlong_as_double(0x7ff8000000000000LL); O.status[p] = DSP_INFEASIBLE; O.iters[p] = it0; }
+        return 0;
+    }
     double c = S.krev * lam;
     double b3 = S.dur * P, b4 = wcf;
     const double b4max = wmax_pos(fabs(b4));

@@ -180,7 +180,10 @@ def wind_battery_pem_optimize(time_points, input_params, verbose=False, want_sol
     sol = get_solver("wind_battery_pem", T, with_battery=with_batt, extant_wind=bool(input_params.get("extant_wind", True)),
                      pem_design=pem_design)
     rp = TP.wind_battery_rparams(T, cf, input_params["wind_mw"], batt, pem_mw=input_params["pem_mw"])
-    rp = rp[0] if rp.shape[0] == 1 else rp
+    if rp.shape[0] == 1:
+        rp = rp[0]
+    elif rp.shape[0] != N:
+        raise ValueError("sizes / capacity factors must be scalar or match the number of LMP scenarios")
     h2 = np.broadcast_to(np.asarray(input_params["h2_price_per_kg"], float), (N,))
     cp = np.ascontiguousarray(np.concatenate([lmp, h2[:, None]], axis=1))
     r = sol.solve_host(cp, rp, want_x=want_solution)

@@ -22,8 +22,8 @@ import os
 _LIB_PATH = Path(os.environ.get("DSP_LP_LIB", Path(__file__).resolve().parent / "csrc" / "libdsp_lp.so"))
 _lib = None
 
-OPTIMAL, MAX_ITER, NUMERICAL = 0, 1, 2
-STATUS_NAMES = {OPTIMAL: "optimal", MAX_ITER: "maxIterations", NUMERICAL: "error"}
+OPTIMAL, MAX_ITER, NUMERICAL, INFEASIBLE = 0, 1, 2, 3
+STATUS_NAMES = {OPTIMAL: "optimal", MAX_ITER: "maxIterations", NUMERICAL: "error", INFEASIBLE: "infeasible"}
 
 KERNEL_AUTO, KERNEL_BAND, KERNEL_STAGE = 0, 1, 2
 
@@ -187,17 +187,27 @@ class BatchLPSolver:
         Stream-ordered on torch's current stream, no synchronisation."""
         import torch
         t = self.t
-        if not cparams.is_cuda or cparams.dtype != torch.float64:
+        if not torch.is_tensor(cparams) or not cparams.is_cuda or cparams.dtype != torch.float64:
             raise ValueError("cparams must be a CUDA float64 tensor (no CPU path)")
+        if cparams.dim() != 2 or cparams.shape[1] != t.Pc:
+            raise ValueError(f"cparams must have shape [N, {t.Pc}], got {tuple(cparams.shape)}")
         cparams = cparams.contiguous()
         N = cparams.shape[0]
         dev = cparams.device
         rstride = 0
         rptr = None
         if t.Pr:
+            if rparams is None or not torch.is_tensor(rparams) or not rparams.is_cuda or rparams.dtype != torch.float64 \
+                    or rparams.device != dev:
+                raise ValueError(f"rparams must be a CUDA float64 tensor on {dev} (template has Pr = {t.Pr})")
+            if tuple(rparams.shape) not in ((t.Pr,), (N, t.Pr)):
+                raise ValueError(f"rparams must have shape [{t.Pr}] or [{N}, {t.Pr}], got {tuple(rparams.shape)}")
             rparams = rparams.contiguous()
             rstride = 0 if rparams.dim() == 1 else t.Pr
             rptr = rparams.data_ptr()
+        if out is not None:
+            self._check_out(out, N, want_x, want_y, lambda a, shape, dt: torch.is_tensor(a) and a.is_cuda and a.device == dev
+                            and a.is_contiguous() and tuple(a.shape) == shape and a.dtype == {"f8": torch.float64, "i4": torch.int32}[dt])
         if out is None:
             out = LPResult(torch.empty(N, dtype=torch.float64, device=dev),
                            torch.empty(N, dtype=torch.int32, device=dev),
@@ -218,13 +228,21 @@ class BatchLPSolver:
         library's staging copy; ``out`` = a previous LPResult of the same shape is reused (no allocation)."""
         t = self.t
         cparams = _f64(np.atleast_2d(cparams))
+        if cparams.ndim != 2 or cparams.shape[1] != t.Pc:
+            raise ValueError(f"cparams must have shape [N, {t.Pc}], got {cparams.shape}")
         N = cparams.shape[0]
         rstride, rptr = 0, None
         if t.Pr:
+            if rparams is None:
+                raise ValueError(f"rparams is required (template has Pr = {t.Pr})")
             rparams = _f64(rparams)
+            if rparams.shape not in ((t.Pr,), (N, t.Pr)):
+                raise ValueError(f"rparams must have shape [{t.Pr}] or [{N}, {t.Pr}], got {rparams.shape}")
             rstride = 0 if rparams.ndim == 1 else t.Pr
             rptr = rparams.ctypes.data_as(C.c_void_p)
         if out is not None:
+            self._check_out(out, N, want_x, want_y, lambda a, shape, dt: isinstance(a, np.ndarray) and a.flags.c_contiguous
+                            and a.shape == shape and a.dtype == np.dtype(dt))
             obj, status, iters, x, y = out.obj, out.status, out.iters, out.x, out.y
         else:
             obj = np.empty(N); status = np.empty(N, np.int32); iters = np.empty(N, np.int32)
@@ -235,6 +253,16 @@ class BatchLPSolver:
                                               vp(obj), vp(status), vp(iters), vp(x), vp(y))
         self._check(rc, "dsp_lp_solve_batch_host")
         return LPResult(obj, status, iters, x, y)
+
+    def _check_out(self, out, N, want_x, want_y, ok):
+        """a reused LPResult must match the batch: a wrong shape / dtype would be an out-of-bounds device write"""
+        t = self.t
+        if not (ok(out.obj, (N,), "f8") and ok(out.status, (N,), "i4") and ok(out.iters, (N,), "i4")):
+            raise ValueError(f"out.obj / out.status / out.iters must be contiguous [{N}] float64 / int32 / int32 buffers")
+        if (out.x is not None and not ok(out.x, (N, t.n), "f8")) or (out.y is not None and not ok(out.y, (N, t.m), "f8")):
+            raise ValueError(f"out.x / out.y must be contiguous float64 [{N}, {t.n}] / [{N}, {t.m}]")
+        if (want_x and out.x is None) or (want_y and out.y is None):
+            raise ValueError("want_x / want_y set but the reused LPResult has no x / y buffer")
 
     @staticmethod
     def pinned_empty(shape, dtype=np.float64):

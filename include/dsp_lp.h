@@ -90,7 +90,13 @@ typedef struct {
     const int32_t *row_idx;             /* [T*4] template row of (t, r1..r4)                                  */
 } dsp_stage_wb_desc;
 
-enum { DSP_OPTIMAL = 0, DSP_MAX_ITER = 1, DSP_NUMERICAL = 2 };
+/* Per-problem status.  DSP_OPTIMAL means: relative primal/dual residuals < feas_tol and relative duality gap < tol; OR, when
+ * the complementarity gap has converged (< tol) while residuals / gap sit at the rounding floor of the ill-conditioned normal
+ * equations, residuals < 10 feas_tol and gap < 10 tol; OR complementarity < 1e-3 tol with residuals < 100 feas_tol and
+ * gap < 1000 tol (the effective worst-case tolerance is therefore 1000 tol = 1e-6 relative on the LP part of the objective at
+ * the defaults; measured worst case on the 560 640 LPs of config C5: 3e-8).  DSP_INFEASIBLE is reported only for a negative
+ * upper bound produced by Umap / rparams (obj = NaN); other infeasible / unbounded LPs end as DSP_MAX_ITER / DSP_NUMERICAL. */
+enum { DSP_OPTIMAL = 0, DSP_MAX_ITER = 1, DSP_NUMERICAL = 2, DSP_INFEASIBLE = 3 };
 enum { DSP_E_ARG = -1, DSP_E_CUDA = -2, DSP_E_SMEM = -3 };
 
 /* Replaces: the per-LP model hand-over inside SolverFactory(..).solve(m) (Pyomo LP/NL writer), done once. */

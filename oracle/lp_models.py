@@ -246,6 +246,43 @@ def wind_battery_raw(lmp, cf, wind_mw, batt_mw, pem_mw=None, h2_price=2.0,
     return B.finish(meta)
 
 
+def wind_pem_closed_form(lmp, cf, wind_mw, pem_mw, h2_price, design_opt=False):
+    """Exact optimum of the wind + PEM price-taker LP with batt_mw = 0 (the sweep of run_pricetaker_wind_PEM.py:37-41): without
+    storage the LP of wind_battery_PEM_LMP.py:217-294 separates per hour --  max lam_t g + kh p  s.t.  g + p <= W cf_t, p <= Pc --
+    so p = min(Pc, W cf_t) where the H2 value kh exceeds the price, and g takes the rest where the price is positive.
+    With design_opt="PEM" the NPV is concave piecewise linear in Pc with breakpoints at the hourly wind outputs: the optimum is
+    the best breakpoint.  Returns dict(NPV, annual_rev_h2, annual_rev_E, pem_kw).  Checked against HiGHS on the raw LP in
+    tests/test_oracle_golden.py; lets the CPU suite pin EVERY PEM > 0 row of the reference's committed table in milliseconds."""
+    lmp = np.asarray(lmp, float); cf = np.asarray(cf, float)
+    T = lmp.size
+    W = wind_mw * 1e3
+    ann = 52.0 / (T / 168.0)
+    kh = h2_price * PEM_ELEC_TO_MOL / H2_MOLS_PER_KG * 3600.0 - PEM_VAR_COST          # $ per kWh sent to the PEM (:276, :268)
+    lam = lmp * 1e-3
+    avail = W * cf
+
+    def evaluate(Pc):
+        Pc = np.atleast_1d(np.asarray(Pc, float))[:, None]
+        pe = np.where((kh > lam) & (kh > 0), np.minimum(Pc, avail), 0.0)
+        g = np.where(lam > 0, avail - pe, 0.0)
+        h2 = (kh * pe).sum(1) * ann
+        el = (lam * g).sum(1) * ann
+        fixed = (W * WIND_OP_COST + Pc[:, 0] * PEM_OP_COST) / 8760.0 * T * ann
+        return h2, el, -(PEM_CAP_COST * Pc[:, 0]) + PA * (h2 + el - fixed)
+
+    if design_opt == "PEM":
+        cand = np.unique(np.concatenate([[0.0], avail]))
+        best = -np.inf
+        for lo in range(0, cand.size, 512):                    # chunks keep the [candidates, T] temporaries small
+            h2, el, npv = evaluate(cand[lo:lo + 512])
+            k = int(np.argmax(npv))
+            if npv[k] > best:
+                best, out = npv[k], dict(NPV=float(npv[k]), annual_rev_h2=float(h2[k]), annual_rev_E=float(el[k]), pem_kw=float(cand[lo + k]))
+        return out
+    h2, el, npv = evaluate(pem_mw * 1e3)
+    return dict(NPV=float(npv[0]), annual_rev_h2=float(h2[0]), annual_rev_E=float(el[0]), pem_kw=pem_mw * 1e3)
+
+
 def wind_battery_report(lp: RawLP, x, lmp):
     """Quantities the reference reads back (wind_battery_LMP.py:252-263, record_results :272-325;
     wind_battery_PEM_LMP.py:300-330)."""

@@ -69,3 +69,13 @@ def test_argument_errors_are_reported_without_a_gpu(cuda_solver_lib):
     assert (o.tol, o.feas_tol, o.max_iter, o.kernel) == (1e-9, 1e-9, 60, solver.KERNEL_AUTO) and o.reg_primal == 1e-8
     sd = solver._StageWB(T=40)
     assert lib.dsp_lp_template_set_stage_wb(None, C.byref(sd)) == -1
+
+
+def test_forced_rebuild_from_source():
+    """build(force=True) recompiles libdsp_lp.so from the sources for sm_100a (nvcc cross-compiles without a GPU) -- the
+    round-end check must not depend on a stale prebuilt library."""
+    import time
+    from dispatches_b200.csrc import build
+    t0 = time.time()
+    lib = build.build(force=True)
+    assert lib.exists() and lib.stat().st_mtime >= t0 - 1.0

@@ -284,6 +284,37 @@ def test_gpu_tracker_known_answer():
 
 
 @pytest.mark.gpu
+def test_gpu_wind_pem_tracker_known_answer():
+    """wind + PEM tracker (wind_PEM_double_loop.py:103-330) through the CUDA path against the reference's known answers
+    (tests/test_wind_PEM_double_loop.py:55-121) and the raw oracle LP."""
+    g = G["wind_pem_tracker"]
+    ref_obj, x = H.solve(DL.wind_pem_tracker_raw(g["market_dispatch"], CF[:4], G["wind_pmax_mw"], g["pem_pmax_mw"]))
+    md = DLH.RenewableGeneratorModelData("309_WIND_1", "Carter", 0, 200)
+    m = DLH.MultiPeriodWindPEM(md, np.tile(CF, 2), wind_pmax_mw=200, pem_pmax_mw=25)
+    tr = DLH.Tracker(m, tracking_horizon=4, n_tracking_hour=1)
+    tr.track_market_dispatch(g["market_dispatch"], date="2020-01-02", hour="00:00")
+    assert tr.objective[0] == pytest.approx(ref_obj, rel=1e-7, abs=1e-6)
+    pem = np.array(g["expected_wind_power"]) - 1e3 * np.array(g["market_dispatch"])                  # :112-119
+    assert tr.fs.sol["pem"][0] == pytest.approx(pem, rel=g["rel"], abs=1.0)
+    assert (tr.fs.sol["pem"][0] + 1e3 * tr.power_output[0]) == pytest.approx(g["expected_wind_power"], rel=g["rel"])   # :93-98
+    assert np.all(np.abs(tr.fs.wind_waste) < 1.0)                                                    # kW; :99-102
+    assert tr.power_output[0] == pytest.approx(g["market_dispatch"], abs=g["abs_power"])
+    # a batch of 64 lock-step simulations with different sizes / series: objective against the raw oracle LP
+    rng = np.random.default_rng(3)
+    N = 64
+    series = np.array([np.roll(np.tile(CF, 2), -int(k)) for k in rng.integers(0, 48, N)])
+    wind = rng.uniform(100, 400, N); pemmw = rng.uniform(5, 60, N)
+    mb = DLH.MultiPeriodWindPEM(md, series, wind_pmax_mw=wind, pem_pmax_mw=pemmw)
+    trb = DLH.Tracker(mb, tracking_horizon=4, n_tracking_hour=1)
+    cf0 = trb.fs.cf.copy()
+    disp = rng.uniform(0, 1, (N, 4)) * wind[:, None] * cf0[:, :4] * 0.9
+    trb.track_market_dispatch(disp, date="d", hour=0)
+    for k in rng.choice(N, 16, replace=False):
+        ref, _ = H.solve(DL.wind_pem_tracker_raw(disp[k], cf0[k, :4], wind[k], pemmw[k]))
+        assert trb.objective[k] == pytest.approx(ref, rel=1e-7, abs=1e-5)
+
+
+@pytest.mark.gpu
 def test_gpu_bidders_known_answers():
     _check_bidders(None)
 

@@ -377,6 +377,47 @@ def test_full_year_wind_pem_against_the_reference_committed_results():
         assert res.annual_rev_h2[k] == pytest.approx(gold["annual_rev_h2"][r], rel=2e-7)
 
 
+def test_full_year_wind_pem_every_committed_row_through_the_cuda_path():
+    """ALL 25 PEM > 0 rows of the reference's committed wind_PEM/wind_PEM_RT_1000.csv through the CUDA path, two batched calls:
+    the 20 fixed-size rows (h2 price and PEM size batched) and the 5 design_opt="PEM" rows (optimal size read back)."""
+    import json
+    from pathlib import Path
+    gold = json.load(open(Path(__file__).parent / "golden" / "wind_pem_golden.json"))["wind_PEM_RT_1000"]
+    p = SC.pool()
+    fixed = [r for r in range(30) if gold["pem_mw"][r] > 0 and r % 6 != 5]
+    design = [r for r in range(30) if r % 6 == 5]
+    assert len(fixed) == 20 and len(design) == 5
+    n = len(fixed)
+    params = {"wind_mw": 847.0, "batt_mw": 0.0, "pem_mw": np.array([gold["pem_mw"][r] for r in fixed]),
+              "h2_price_per_kg": np.array([gold["h2_price_per_kg"][r] for r in fixed]), "design_opt": False,
+              "extant_wind": True, "wind_resource": np.tile(p["pq1000_rt_cf"], (n, 1)), "DA_LMPs": np.tile(p["pq1000_rt_lmp"], (n, 1))}
+    res = PT.wind_battery_pem_optimize(8784, params)
+    assert (res.status == S.OPTIMAL).all()
+    for k, r in enumerate(fixed):
+        scale = TP.PEM_CAP_COST * gold["pem_mw"][r] * 1e3 + TP.PA * (res.annual_rev_h2[k] + abs(res.annual_elec_revenue[k]))
+        assert res.NPV[k] == pytest.approx(gold["NPV"][r], rel=2e-7, abs=1e-7 * scale), r
+        assert res.annual_rev_h2[k] == pytest.approx(gold["annual_rev_h2"][r], rel=1e-6), r
+    n = len(design)
+    params.update({"pem_mw": 355.0, "h2_price_per_kg": np.array([gold["h2_price_per_kg"][r] for r in design]), "design_opt": "PEM",
+                   "wind_resource": np.tile(p["pq1000_rt_cf"], (n, 1)), "DA_LMPs": np.tile(p["pq1000_rt_lmp"], (n, 1))})
+    res = PT.wind_battery_pem_optimize(8784, params)
+    assert (res.status == S.OPTIMAL).all()
+    for k, r in enumerate(design):
+        assert res.sizes["pem_kw"][k] * 1e-3 == pytest.approx(gold["pem_mw"][r], abs=0.06), r      # the table rounds to 0.1 MW
+        assert res.NPV[k] == pytest.approx(gold["NPV"][r], rel=1e-6), r
+
+
+def test_c2_full_batch_objective_parity_1e6(wb):
+    """BASELINE config C2 in full: all 10 000 objectives within 1e-6 relative of the oracle (HiGHS on the raw LP)."""
+    t, sol = wb
+    lmp, cf, W, P = SC.c2(10000)
+    rp = TP.wind_battery_rparams(24, cf, W, P)[0]
+    r = sol.solve_host(lmp, rp)
+    assert (r.status == S.OPTIMAL).all()
+    ref, _, _ = H.solve_batch("wind_battery", lmp, kwargs=dict(cf=cf, wind_mw=W, batt_mw=P))
+    assert rel_err(r.obj, ref).max() < REL
+
+
 def test_long_horizon_wind_battery_quarter_year():
     """run_pricetaker_wind_battery.run_design's kind of LP (the reference uses n_time_points = 8736): a 2184-period
     wind+battery LP against the oracle; the throughput column grows with the horizon (scale-invariant proximal term)."""
