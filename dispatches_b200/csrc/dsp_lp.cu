@@ -27,7 +27,7 @@
 #include <string>
 #include <vector>
 
-#define DSP_VERSION "dsp_lp 0.1 (sm_100a band-IPM)"
+#define DSP_VERSION "dsp_lp 0.2 (sm_100a band-IPM + stage kernels)"
 
 namespace {
 
@@ -561,6 +561,31 @@ __global__ void __launch_bounds__(32 * DSP_STAGE_WPB, DSP_STAGE_MINB) dsp_ipm_st
     }
 }
 
+}  // namespace
+
+#include "dsp_stage2.cuh"
+
+namespace {
+// stage kernel, generation 2: 32/L LPs per warp, P periods per lane, one warp per CTA (see dsp_stage2.cuh).  The register
+// budget is the full 255 (65536 / (7 CTAs x 32 threads) = 292): occupancy is set by the 31 KB of shared memory per warp.
+constexpr int kStage2Warps = 8;        // warps per CTA = per SM: 8 x 27.9 KB of shared memory, 8 x 32 x 255 registers
+template <int L, int P, bool SYNC>
+__global__ void __launch_bounds__(32 * kStage2Warps, 1) dsp_ipm_stage2_wb_kernel(const stage2::Params Q) {
+    extern __shared__ __align__(16) double s2_smem[];
+    stage2::warp_body<L, P, SYNC>(Q, s2_smem + (threadIdx.x >> 5) * stage2::SmemDoubles<P>::value, threadIdx.x & 31);
+}
+
+struct Stage2Geom { int L, P; };
+inline Stage2Geom stage2_geometry(int T) {
+    if (T <= 6) return {2, 3};
+    if (T <= 12) return {4, 3};
+    if (T <= 24) return {8, 3};
+    if (T <= 32) return {16, 2};
+    if (T <= 48) return {16, 3};
+    return {32, 3};                  // T <= 96
+}
+constexpr int kStage2MaxT = 96;
+
 // FP64 FMA micro-benchmark: the measured denominator of the FP64 roofline fraction bench.py reports (the driver's
 // MEASURED_PEAKS.json has HBM and bf16 peaks only).  8 independent DFMA chains per thread.
 __global__ void __launch_bounds__(256) dsp_fp64_peak_kernel(double *out, int iters, double a, double b) {
@@ -611,6 +636,7 @@ struct dsp_template {
     mutable size_t ws_bytes;
     stagewb::StageParams sp;
     int stage_blocks_per_sm;
+    int stage2_blocks_per_sm;      // generation-2 stage kernel: CTAs (= warps) per SM for this template's (L, P)
     int device;
     int sm_count;
     int smem_optin;
@@ -626,6 +652,27 @@ struct dsp_template {
     int64_t cap_rp_rows;
     cudaStream_t stream, stream2;
 };
+
+namespace {
+#define S2_DISPATCH(CALL)                                                   \
+    do {                                                                    \
+        if (g.L == 2) { CALL(2, 3); }                                       \
+        else if (g.L == 4) { CALL(4, 3); }                                  \
+        else if (g.L == 8) { CALL(8, 3); }                                  \
+        else if (g.L == 16 && g.P == 2) { CALL(16, 2); }                    \
+        else if (g.L == 16) { CALL(16, 3); }                                \
+        else { CALL(32, 3); }                                               \
+    } while (0)
+const void *stage2_function(const Stage2Geom &g, bool sync) {
+#define S2_FN(l, p) return sync ? (const void *)dsp_ipm_stage2_wb_kernel<l, p, true> : (const void *)dsp_ipm_stage2_wb_kernel<l, p, false>
+    S2_DISPATCH(S2_FN);
+#undef S2_FN
+    return nullptr;
+}
+size_t stage2_smem_bytes(const Stage2Geom &g) {
+    return (size_t)(g.P == 2 ? stage2::smem_doubles_per_warp<2>() : stage2::smem_doubles_per_warp<3>()) * 8;
+}
+}  // namespace
 
 extern "C" {
 
@@ -755,7 +802,7 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     } guard{T};
     memset(&T->kp, 0, sizeof(KParams));
     T->cap_N = 0; T->cap_x = T->cap_y = false; T->cap_rp_rows = 0;
-    T->has_stage = false; T->stage_blocks_per_sm = 0; T->ws = nullptr; T->ws_bytes = 0;
+    T->has_stage = false; T->stage_blocks_per_sm = 0; T->stage2_blocks_per_sm = 0; T->ws = nullptr; T->ws_bytes = 0;
     T->h_cp = T->h_rp = T->h_obj = T->h_x = T->h_y = nullptr; T->h_status = T->h_iters = nullptr;
     T->d_cp = T->d_rp = T->d_obj = T->d_x = T->d_y = nullptr; T->d_status = T->d_iters = nullptr;
     T->stream = nullptr; T->stream2 = nullptr;
@@ -837,7 +884,7 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
 }
 
 int dsp_lp_template_set_stage_wb(dsp_template *T, const dsp_stage_wb_desc *d) {
-    if (!T || !d || d->T < 1 || d->T > 32) { g_err = "dsp_lp_template_set_stage_wb: need 1 <= T <= 32"; return DSP_E_ARG; }
+    if (!T || !d || d->T < 1 || d->T > kStage2MaxT) { g_err = "dsp_lp_template_set_stage_wb: need 1 <= T <= 96"; return DSP_E_ARG; }
     if (T->kp.Pc < d->T || T->kp.Pr <= std::max(d->wcf_off + d->T - 1, d->p_off)) {
         g_err = "dsp_lp_template_set_stage_wb: parameter layout does not fit the template";
         return DSP_E_ARG;
@@ -856,6 +903,16 @@ int dsp_lp_template_set_stage_wb(dsp_template *T, const dsp_stage_wb_desc *d) {
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dsp_ipm_stage_wb_kernel, 32 * DSP_STAGE_WPB, 0));
     T->stage_blocks_per_sm = std::max(nb, 1);
+    {
+        const Stage2Geom g = stage2_geometry(d->T);
+        const size_t smem = stage2_smem_bytes(g) * kStage2Warps;
+        for (int sync = 0; sync < 2; ++sync) {
+            const void *fn = stage2_function(g, sync != 0);
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+        T->stage2_blocks_per_sm = 1;
+    }
     T->has_stage = true;
     return 0;
 }
@@ -937,8 +994,42 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
     K.tol = o.tol; K.feas_tol = o.feas_tol; K.step_frac = o.step_frac; K.reg = o.reg_primal; K.max_iter = o.max_iter;
     K.obj = obj; K.status = status; K.iters = iters; K.x_out = x; K.y_out = y;
     K.ticket = ticket;
-    if (T->has_stage && o.kernel != DSP_KERNEL_BAND) {
-        // stage kernel: no shared memory; persistent warps, one LP per warp at a time
+    if (T->has_stage && (o.kernel == DSP_KERNEL_AUTO || o.kernel == DSP_KERNEL_STAGE)) {
+        // generation-2 stage kernel: 32/L LPs per warp, persistent one-warp CTAs, LP groups refill from the ticket counter
+        const Stage2Geom g = stage2_geometry(T->sp.T);
+        const int per_warp = 32 / g.L;
+        // one persistent CTA per SM; its warps (up to kStage2Warps) run the phases of an IPM round in step
+        int wmax = kStage2Warps;
+        bool sync = true;
+        if (const char *e = getenv("DSP_STAGE2_WARPS")) wmax = std::min(kStage2Warps, std::max(1, atoi(e)));   // experiments only
+        if (const char *e = getenv("DSP_STAGE2_SYNC")) sync = atoi(e) != 0;
+        const long long warps_needed = (N + per_warp - 1) / per_warp;
+        const long long blocks = std::max<long long>(1, std::min<long long>(T->sm_count, warps_needed));
+        const int wpb = (int)std::min<long long>(wmax, (warps_needed + blocks - 1) / blocks);
+        const size_t smem = stage2_smem_bytes(g) * wpb;
+        stage2::Params Q;
+        Q.N = N; Q.cparams = cparams; Q.rparams = rparams; Q.rstride = rparams_stride; Q.Pc = K.Pc; Q.Pr = K.Pr;
+        Q.omap = K.omap; Q.ocmap = K.ocmap; Q.o0 = K.o0;
+        Q.tol = o.tol; Q.feas_tol = o.feas_tol; Q.step_frac = o.step_frac; Q.reg = o.reg_primal; Q.max_iter = o.max_iter;
+        Q.obj = obj; Q.x_out = x; Q.y_out = y; Q.status = status; Q.iters = iters; Q.n = K.n; Q.m = K.m; Q.ticket = ticket;
+        const stagewb::StageParams &S = T->sp;
+        Q.T = S.T; Q.a = S.a; Q.binv = S.binv; Q.hf = S.hf; Q.dl = S.dl; Q.dur = S.dur; Q.krev = S.krev;
+        Q.wcf_off = S.wcf_off; Q.p_off = S.p_off; Q.col_idx = S.col_idx; Q.row_idx = S.row_idx;
+        CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
+#define S2_LAUNCH(l, p)                                                                                      \
+        if (sync) dsp_ipm_stage2_wb_kernel<l, p, true><<<(unsigned)blocks, 32 * wpb, smem, st>>>(Q);             \
+        else dsp_ipm_stage2_wb_kernel<l, p, false><<<(unsigned)blocks, 32 * wpb, smem, st>>>(Q)
+        S2_DISPATCH(S2_LAUNCH);
+#undef S2_LAUNCH
+        CK(cudaGetLastError());
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_launches++;
+        g_last_grid = (int)blocks; g_last_block = 32 * wpb; g_last_smem = (int)smem; g_last_ppc = per_warp * wpb;
+        return 0;
+    }
+    if (T->has_stage && o.kernel == DSP_KERNEL_STAGE_V1) {
+        if (T->sp.T > 32) { g_err = "dsp_lp_solve_batch: the lane-per-period stage kernel needs T <= 32"; return DSP_E_ARG; }
+        // generation-1 stage kernel (lane per period): no shared memory; persistent warps, one LP per warp at a time
         const int wpb = DSP_STAGE_WPB;
         long long per_sm = T->stage_blocks_per_sm;
         if (const char *e = getenv("DSP_STAGE_BLOCKS_PER_SM")) per_sm = std::max(1, atoi(e));   // experiments only
@@ -951,7 +1042,7 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         g_last_grid = (int)blocks; g_last_block = wpb * 32; g_last_smem = 0; g_last_ppc = wpb;
         return 0;
     }
-    if (o.kernel == DSP_KERNEL_STAGE) {
+    if (o.kernel == DSP_KERNEL_STAGE || o.kernel == DSP_KERNEL_STAGE_V1) {
         g_err = "dsp_lp_solve_batch: the template has no stage descriptor";
         return DSP_E_ARG;
     }

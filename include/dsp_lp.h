@@ -71,16 +71,18 @@ typedef struct {
     int32_t device;       /* reserved (the current CUDA device is used); keep -1        */
     double  reg_primal;   /* proximal regularisation of D^-1 in scaled units (default 1e-8; applied as reg/max(1,x^2)): caps the scaling
                              of never-binding columns (throughput, slacks) so A D A' stays factorisable    */
-    int32_t kernel;       /* DSP_KERNEL_AUTO (stage kernel when the template has one), _BAND, _STAGE */
+    int32_t kernel;       /* DSP_KERNEL_AUTO (stage kernel when the template has one), _BAND, _STAGE, _STAGE_V1 */
 } dsp_opts;
 
-enum { DSP_KERNEL_AUTO = 0, DSP_KERNEL_BAND = 1, DSP_KERNEL_STAGE = 2 };
+enum { DSP_KERNEL_AUTO = 0, DSP_KERNEL_BAND = 1, DSP_KERNEL_STAGE = 2 /* generation 2: several LPs per warp */,
+       DSP_KERNEL_STAGE_V1 = 3 /* generation 1: lane per period, T <= 32 (kept as an independent implementation for tests) */ };
 
 /* Stage descriptor of the wind+battery price-taker flowsheet (wind_battery_LMP.py:172-267, reduced form):
- * T <= 32 periods, per period the columns g,i,o,s,e,p,q and rows r1 (state_evolution, battery.py:145-149),
+ * T <= 96 periods, per period the columns g,i,o,s,e,p,q and rows r1 (state_evolution, battery.py:145-149),
  * r2 (accumulate_energy_throughput :151-153), r3 (state_of_charge_bounds :155-157, slack p),
- * r4 (wind_power.py:120-122 + splitter, slack q).  Lets dsp_lp_solve_batch run the register-resident
- * lane-per-period kernel instead of the generic band kernel; results are identical up to rounding.    */
+ * r4 (wind_power.py:120-122 + splitter, slack q).  Lets dsp_lp_solve_batch run the stage kernels (several LPs per warp,
+ * iterate in registers, partitioned block elimination: csrc/dsp_stage2.cuh) instead of the generic band kernel; results
+ * are identical up to rounding.    */
 typedef struct {
     int32_t T;
     double a, binv, half, delta, dur;   /* charging_eta, 1/discharging_eta, 1/2, degradation_rate, duration  */

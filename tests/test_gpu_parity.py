@@ -95,22 +95,29 @@ def test_c2_full_batch_certificates(wb):
 
 
 def test_stage_and_band_kernels_agree(wb):
-    """Two independent CUDA implementations of the same algorithm: the generic band kernel (shared memory, band
-    LDL') and the stage kernel (registers, local elimination + twisted block LDL')."""
+    """Three independent CUDA implementations of the same algorithm: the generic band kernel (shared memory, band LDL'), the
+    lane-per-period stage kernel (generation 1: registers, twisted block LDL') and the several-LPs-per-warp stage kernel
+    (generation 2: partitioned block elimination) -- same iterates up to the rounding of three elimination orders."""
     t, sol = wb
     assert sol.has_stage
     band = S.BatchLPSolver(t, kernel=S.KERNEL_BAND)
+    v1 = S.BatchLPSolver(t, kernel=S.KERNEL_STAGE_V1)
     lmp, cf, W, P = SC.c2(2000)
     rp = TP.wind_battery_rparams(24, cf, W, P)[0]
     a = sol.solve_host(lmp, rp, want_x=True, want_y=True)
-    assert S.last_launch()["smem_bytes"] == 0                 # stage kernel: registers only
+    assert S.last_launch()["problems_per_cta"] == 4            # generation 2: four LPs per warp at T = 24
     b = band.solve_host(lmp, rp, want_x=True, want_y=True)
-    assert S.last_launch()["smem_bytes"] > 0
-    assert (a.status == S.OPTIMAL).all() and (b.status == S.OPTIMAL).all()
-    assert rel_err(a.obj, b.obj).max() < 1e-7
-    assert (a.iters == b.iters).mean() > 0.97
-    scale = np.abs(t.instantiate(lmp[0], rp)[1]).max()
-    assert np.abs(a.x @ t.A.T - t.instantiate(lmp[0], rp)[1]).max() <= 1e-7 * scale
+    assert S.last_launch()["smem_bytes"] > 40000
+    c = v1.solve_host(lmp, rp, want_x=True, want_y=True)
+    assert S.last_launch()["smem_bytes"] == 0                  # generation 1: registers only
+    for r in (a, b, c):
+        assert (r.status == S.OPTIMAL).all()
+    assert rel_err(a.obj, b.obj).max() < 1e-7 and rel_err(a.obj, c.obj).max() < 1e-7
+    assert (a.iters == b.iters).mean() > 0.97 and (a.iters == c.iters).mean() > 0.97
+    b0 = t.instantiate(lmp[0], rp)[1]
+    scale = np.abs(b0).max()
+    assert np.abs(a.x @ t.A.T - b0).max() <= 1e-7 * scale
+    assert np.abs(a.x - c.x).max() <= 1e-6 * scale and np.abs(a.y - c.y).max() <= 1e-6 * max(1.0, np.abs(c.y).max())
 
 
 def test_c5_design_sweep_sample_all_optimal(wb):
@@ -277,16 +284,17 @@ def test_random_designs_and_prices_fuzz(wb):
     assert rel_err(r.obj, ref).max() < REL
 
 
-@pytest.mark.parametrize("T", [2, 5, 12, 31, 32])
+@pytest.mark.parametrize("T", [2, 5, 7, 12, 13, 23, 31, 32, 33, 48, 49, 96])
 def test_stage_kernel_other_horizons(T):
-    """The stage kernel's run-time-T path (only T = 24 is compiled with a fixed horizon): odd / even / full-warp
-    horizons against the band kernel and the oracle."""
+    """Every (lanes per LP, periods per lane) instantiation of the stage kernel -- (2,3) (4,3) (8,3) (16,2) (16,3) (32,3) -- at
+    horizons that fill it exactly and that leave periods / lanes idle, against the band kernel and the oracle."""
     t = TP.wind_battery(T)
     stage = S.BatchLPSolver(t, kernel=S.KERNEL_STAGE)
     band = S.BatchLPSolver(t, kernel=S.KERNEL_BAND)
     p = SC.pool()
     rng = np.random.default_rng(T)
     N = 24
+    N = 24 if T <= 32 else 40
     h0 = rng.integers(0, 8000, N)
     idx = h0[:, None] + np.arange(T)[None, :]
     lmp = p["dalmp_303"][idx] * rng.lognormal(0, 0.3, (N, T))
