@@ -67,6 +67,7 @@ struct KParams {
     int prob_off;                 // byte offset of the first per-warp region
     int band_doubles;             // doubles of the (dy, Mb) tail of a work region: what the LDL' / substitution sweeps touch
     int hybrid;                   // workspace mode with the (dy, Mb) tail in shared memory (sweeps at shared-memory latency)
+    const int *xperm, *yperm;     // non-null: x_out / y_out index of internal column j / row i (dsp_lp_template_create_csr)
 };
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -183,7 +184,7 @@ template <int W>
 __device__ __forceinline__ void band_solve(const double *Mb, double *v, int m, int lane) {
     constexpr int W1 = W + 1;
     const int r = (lane % W) + 1;                 // lanes >= W idle in the sweeps (W <= 16 < 32)
-    const bool on = lane < W;
+    const bool on = lane < W;                     // W <= 32
     for (int j = 0; j < m; ++j) {                 // forward: L t = r  (column sweeps)
         const double t = v[j] * Mb[j * W1];
         if (on) v[j + r] -= Mb[(j + r) * W1 + r] * t;
@@ -462,11 +463,13 @@ __device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long lo
     }
     if (P.x_out) {
         double *xo = P.x_out + p * (long long)n;
-        for (int j = lane; j < n; j += 32) xo[j] = W.x[j] * beta_b;
+        if (P.xperm) { for (int j = lane; j < n; j += 32) xo[P.xperm[j]] = W.x[j] * beta_b; }
+        else { for (int j = lane; j < n; j += 32) xo[j] = W.x[j] * beta_b; }
     }
     if (P.y_out) {
         double *yo = P.y_out + p * (long long)m;
-        for (int i = lane; i < m; i += 32) yo[i] = W.y[i] * beta_c;
+        if (P.yperm) { for (int i = lane; i < m; i += 32) yo[P.yperm[i]] = W.y[i] * beta_c; }
+        else { for (int i = lane; i < m; i += 32) yo[i] = W.y[i] * beta_c; }
     }
     __syncwarp();
     *status_out = status;
@@ -568,7 +571,10 @@ __global__ void __launch_bounds__(32 * DSP_STAGE_WPB, DSP_STAGE_MINB) dsp_ipm_st
 namespace {
 // stage kernel, generation 2: 32/L LPs per warp, P periods per lane, one warp per CTA (see dsp_stage2.cuh).  The register
 // budget is the full 255 (65536 / (7 CTAs x 32 threads) = 292): occupancy is set by the 31 KB of shared memory per warp.
-constexpr int kStage2Warps = 8;        // warps per CTA = per SM: 8 x 27.9 KB of shared memory, 8 x 32 x 255 registers
+#ifndef DSP_S2_WARPS
+#define DSP_S2_WARPS 8
+#endif
+constexpr int kStage2Warps = DSP_S2_WARPS;        // warps per CTA = per SM: 8 x 27.9 KB of shared memory, 8 x 32 x 255 registers
 template <int L, int P, bool SYNC>
 __global__ void __launch_bounds__(32 * kStage2Warps, 1) dsp_ipm_stage2_wb_kernel(const stage2::Params Q) {
     extern __shared__ __align__(16) double s2_smem[];
@@ -577,6 +583,10 @@ __global__ void __launch_bounds__(32 * kStage2Warps, 1) dsp_ipm_stage2_wb_kernel
 
 struct Stage2Geom { int L, P; };
 inline Stage2Geom stage2_geometry(int T) {
+    if (const char *e = getenv("DSP_STAGE2_GEOM")) {       // experiments only: "L,P"
+        int l = 0, p = 0;
+        if (sscanf(e, "%d,%d", &l, &p) == 2 && l * p >= T && (p == 3 || (l == 16 && p == 2))) return {l, p};
+    }
     if (T <= 6) return {2, 3};
     if (T <= 12) return {4, 3};
     if (T <= 24) return {8, 3};
@@ -641,6 +651,7 @@ struct dsp_template {
     int sm_count;
     int smem_optin;
     std::vector<void *> dev_allocs;
+    std::vector<int> col_perm, row_perm;     // dsp_lp_template_create_csr: caller index of internal column / row
     unsigned long long *ticket;
     // host-call staging (pinned) and device buffers, grown on demand
     int64_t cap_N;
@@ -739,10 +750,10 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     }
     const int m = D->m, n = D->n, nb = D->nb, w = D->w;
     const int nnz = D->A_ptr[m];
-    // the kernels are instantiated for half bandwidths 1, 2, 4, 8, 16: pad the band storage to the next one
+    // the kernels are instantiated for half bandwidths 1, 2, 4, 8, 16, 32: pad the band storage to the next one
     int wt = 1;
     while (wt < w) wt *= 2;
-    if (wt > 16) { g_err = "dsp_lp_template_create: half bandwidth of A*A' above 16 is not supported"; return DSP_E_ARG; }
+    if (wt > 32) { g_err = "dsp_lp_template_create: half bandwidth of A*A' above 32 is not supported"; return DSP_E_ARG; }
     const int nent = m * (wt + 1);
     const int nasm = D->asm_ptr[m * (w + 1)];
     std::vector<int> asm_ptr_pad(nent + 1, 0);
@@ -876,6 +887,9 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<32, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
+    CK(cudaFuncSetAttribute(dsp_ipm_band_kernel<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_optin));
     CK(cudaStreamCreateWithFlags(&T->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&T->stream2, cudaStreamNonBlocking));
     guard.t = nullptr;
@@ -1097,9 +1111,13 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
                 else if (hot_in_smem) dsp_ipm_band_kernel<8, false, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
                 else dsp_ipm_band_kernel<8, false, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
                 break;
-        default: if (ws_mode) dsp_ipm_band_kernel<16, true, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+        case 16: if (ws_mode) dsp_ipm_band_kernel<16, true, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
                  else if (hot_in_smem) dsp_ipm_band_kernel<16, false, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
-                else dsp_ipm_band_kernel<16, false, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                 else dsp_ipm_band_kernel<16, false, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                 break;
+        default: if (ws_mode) dsp_ipm_band_kernel<32, true, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                 else if (hot_in_smem) dsp_ipm_band_kernel<32, false, true><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
+                 else dsp_ipm_band_kernel<32, false, false><<<(unsigned)ctas, (unsigned)(warps * 32), smem, st>>>(K);
                  break;
     }
     CK(cudaGetLastError());
@@ -1248,6 +1266,201 @@ int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, c
         if (x) memcpy(x, T->h_x, (size_t)N * K.n * 8);
         if (y) memcpy(y, T->h_y, (size_t)N * K.m * 8);
     }
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Template from plain CSR: everything dsp_lp_template_create expects from its caller -- bounded columns first, a
+// bandwidth-reducing row order for A A', the assembly list of the band of A D A' -- is derived here, so that a C caller
+// (or the Pyomo walker) hands over nothing but the standard-form LP.  Host-only analysis: no CUDA call before the upload.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct CsrAnalysis {
+    std::vector<int> col_perm, row_perm;      // internal -> caller
+    int nb = 0, w = 0, w_natural = 0, w_rcm = 0;
+    std::vector<int> A_ptr, A_idx;            // permuted CSR
+    std::vector<double> A_val;
+    std::vector<int> asm_ptr, asm_col;
+    std::vector<double> asm_val;
+};
+
+int bandwidth_of(const std::vector<std::vector<int>> &adj, const std::vector<int> &pos) {
+    int w = 0;
+    for (size_t i = 0; i < adj.size(); ++i)
+        for (int j : adj[i]) w = std::max(w, std::abs(pos[i] - pos[j]));
+    return w;
+}
+
+// reverse Cuthill-McKee on the row graph of A A' (start of every component: a pseudo-peripheral node of minimum degree)
+std::vector<int> rcm_order(const std::vector<std::vector<int>> &adj) {
+    const int m = (int)adj.size();
+    std::vector<int> order; order.reserve(m);
+    std::vector<char> seen(m, 0);
+    std::vector<int> by_deg(m);
+    for (int i = 0; i < m; ++i) by_deg[i] = i;
+    std::stable_sort(by_deg.begin(), by_deg.end(), [&](int a, int b) { return adj[a].size() < adj[b].size(); });
+    auto bfs = [&](int start, std::vector<int> &out, std::vector<char> &mark) {
+        out.clear(); out.push_back(start); mark[start] = 1;
+        for (size_t h = 0; h < out.size(); ++h) {
+            std::vector<int> nb;
+            for (int v : adj[out[h]]) if (!mark[v]) { mark[v] = 1; nb.push_back(v); }
+            std::stable_sort(nb.begin(), nb.end(), [&](int a, int b) { return adj[a].size() < adj[b].size(); });
+            out.insert(out.end(), nb.begin(), nb.end());
+        }
+    };
+    for (int s0 : by_deg) {
+        if (seen[s0]) continue;
+        int start = s0;
+        std::vector<int> comp;
+        for (int pass = 0; pass < 3; ++pass) {         // walk towards a pseudo-peripheral node
+            std::vector<char> mark(seen);
+            bfs(start, comp, mark);
+            int last = comp.back();
+            if (last == start) break;
+            start = last;
+        }
+        std::vector<int> comp2;
+        bfs(start, comp2, seen);
+        order.insert(order.end(), comp2.begin(), comp2.end());
+    }
+    std::reverse(order.begin(), order.end());
+    return order;
+}
+
+int analyze_csr(const dsp_lp_desc *D, CsrAnalysis &R) {
+    if (!D || D->m <= 0 || D->n <= 0 || !D->A_ptr || !D->A_idx || !D->A_val || !D->u0) { g_err = "dsp_lp_analyze: bad descriptor"; return DSP_E_ARG; }
+    const int m = D->m, n = D->n;
+    const int nnz = D->A_ptr[m];
+    for (int q = 0; q < nnz; ++q)
+        if (D->A_idx[q] < 0 || D->A_idx[q] >= n) { g_err = "dsp_lp_analyze: A_idx out of range"; return DSP_E_ARG; }
+    // 1. bounded columns first (stable)
+    R.col_perm.clear();
+    for (int j = 0; j < n; ++j) if (D->u0[j] < 1e300) R.col_perm.push_back(j);
+    R.nb = (int)R.col_perm.size();
+    for (int j = 0; j < n; ++j) if (!(D->u0[j] < 1e300)) R.col_perm.push_back(j);
+    std::vector<int> col_pos(n);
+    for (int k = 0; k < n; ++k) col_pos[R.col_perm[k]] = k;
+    // 2. row graph of A A'
+    std::vector<std::vector<int>> rows_of_col(n);
+    for (int i = 0; i < m; ++i)
+        for (int q = D->A_ptr[i]; q < D->A_ptr[i + 1]; ++q) rows_of_col[D->A_idx[q]].push_back(i);
+    std::vector<std::vector<int>> adj(m);
+    for (int j = 0; j < n; ++j)
+        for (int a : rows_of_col[j])
+            for (int b : rows_of_col[j])
+                if (a != b) adj[a].push_back(b);
+    for (auto &v : adj) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    std::vector<int> nat(m), pos(m);
+    for (int i = 0; i < m; ++i) nat[i] = pos[i] = i;
+    R.w_natural = bandwidth_of(adj, pos);
+    std::vector<int> rcm = rcm_order(adj);
+    for (int k = 0; k < m; ++k) pos[rcm[k]] = k;
+    R.w_rcm = bandwidth_of(adj, pos);
+    R.row_perm = (R.w_natural <= R.w_rcm) ? nat : rcm;
+    R.w = std::min(R.w_natural, R.w_rcm);
+    std::vector<int> row_pos(m);
+    for (int k = 0; k < m; ++k) row_pos[R.row_perm[k]] = k;
+    // 3. permuted CSR with sorted column indices
+    R.A_ptr.assign(m + 1, 0); R.A_idx.resize(nnz); R.A_val.resize(nnz);
+    for (int k = 0; k < m; ++k) R.A_ptr[k + 1] = R.A_ptr[k] + (D->A_ptr[R.row_perm[k] + 1] - D->A_ptr[R.row_perm[k]]);
+    for (int k = 0; k < m; ++k) {
+        const int i = R.row_perm[k];
+        std::vector<std::pair<int, double>> ent;
+        for (int q = D->A_ptr[i]; q < D->A_ptr[i + 1]; ++q) ent.emplace_back(col_pos[D->A_idx[q]], D->A_val[q]);
+        std::sort(ent.begin(), ent.end());
+        for (size_t e = 0; e < ent.size(); ++e) { R.A_idx[R.A_ptr[k] + e] = ent[e].first; R.A_val[R.A_ptr[k] + e] = ent[e].second; }
+    }
+    // 4. assembly list of the lower band of M = A D A':  M[i][i-k] = sum coef * d[col]
+    const int w = R.w;
+    std::vector<std::vector<std::pair<int, double>>> ent((size_t)m * (w + 1));
+    std::vector<std::vector<std::pair<int, double>>> col_rows(n);       // (new row, value) per new column
+    for (int k = 0; k < m; ++k)
+        for (int q = R.A_ptr[k]; q < R.A_ptr[k + 1]; ++q) col_rows[R.A_idx[q]].emplace_back(k, R.A_val[q]);
+    for (int j = 0; j < n; ++j)
+        for (auto &ra : col_rows[j])
+            for (auto &rb : col_rows[j])
+                if (rb.first <= ra.first) ent[(size_t)ra.first * (w + 1) + (ra.first - rb.first)].emplace_back(j, ra.second * rb.second);
+    R.asm_ptr.assign((size_t)m * (w + 1) + 1, 0);
+    R.asm_col.clear(); R.asm_val.clear();
+    for (size_t e = 0; e < ent.size(); ++e) {
+        R.asm_ptr[e + 1] = R.asm_ptr[e] + (int)ent[e].size();
+        for (auto &cv : ent[e]) { R.asm_col.push_back(cv.first); R.asm_val.push_back(cv.second); }
+    }
+    return 0;
+}
+
+// rows of a dsp_param_map re-ordered: out row k = in row perm[k]
+void permute_map(const dsp_param_map &in, const std::vector<int> &perm, int nrows_out, std::vector<int> &ptr, std::vector<int> &idx, std::vector<double> &val) {
+    ptr.assign(nrows_out + 1, 0); idx.clear(); val.clear();
+    for (int k = 0; k < nrows_out; ++k) {
+        const int r = perm[k];
+        if (in.ptr) for (int q = in.ptr[r]; q < in.ptr[r + 1]; ++q) { idx.push_back(in.idx[q]); val.push_back(in.val[q]); }
+        ptr[k + 1] = (int)idx.size();
+    }
+}
+}  // namespace
+
+int dsp_lp_analyze_csr(const dsp_lp_desc *D, int32_t *nb, int32_t *w, int32_t *w_natural, int32_t *w_rcm, int32_t *col_perm, int32_t *row_perm) {
+    CsrAnalysis R;
+    int rc = analyze_csr(D, R);
+    if (rc) return rc;
+    if (nb) *nb = R.nb;
+    if (w) *w = R.w;
+    if (w_natural) *w_natural = R.w_natural;
+    if (w_rcm) *w_rcm = R.w_rcm;
+    if (col_perm) std::copy(R.col_perm.begin(), R.col_perm.end(), col_perm);
+    if (row_perm) std::copy(R.row_perm.begin(), R.row_perm.end(), row_perm);
+    return 0;
+}
+
+int dsp_lp_template_create_csr(const dsp_lp_desc *D, dsp_template **out) {
+    if (!out) { g_err = "dsp_lp_template_create_csr: out is NULL"; return DSP_E_ARG; }
+    CsrAnalysis R;
+    int rc = analyze_csr(D, R);
+    if (rc) return rc;
+    const int m = D->m, n = D->n, nb = R.nb;
+    std::vector<double> c0(n), u0(std::max(nb, 1)), b0(m);
+    for (int k = 0; k < n; ++k) c0[k] = D->c0 ? D->c0[R.col_perm[k]] : 0.0;
+    for (int k = 0; k < nb; ++k) u0[k] = D->u0[R.col_perm[k]];
+    for (int k = 0; k < m; ++k) b0[k] = D->b0 ? D->b0[R.row_perm[k]] : 0.0;
+    std::vector<int> cp, ci, bp, bi, up, ui;
+    std::vector<double> cv, bv, uv;
+    permute_map(D->cmap, R.col_perm, n, cp, ci, cv);
+    permute_map(D->bmap, R.row_perm, m, bp, bi, bv);
+    permute_map(D->umap, R.col_perm, nb, up, ui, uv);
+    std::vector<double> zPr(std::max(D->Pr, 1), 0.0), zPc(std::max(D->Pc, 1), 0.0);
+    auto nz = [](std::vector<int> &v) { if (v.empty()) v.push_back(0); return v.data(); };
+    auto nzd = [](std::vector<double> &v) { if (v.empty()) v.push_back(0.0); return v.data(); };
+    dsp_template_desc d;
+    memset(&d, 0, sizeof(d));
+    d.m = m; d.n = n; d.nb = nb; d.w = R.w; d.Pc = D->Pc; d.Pr = D->Pr;
+    d.A_ptr = R.A_ptr.data(); d.A_idx = R.A_idx.data(); d.A_val = R.A_val.data();
+    d.asm_ptr = R.asm_ptr.data(); d.asm_col = nz(R.asm_col); d.asm_val = nzd(R.asm_val);
+    d.c0 = c0.data(); d.cmap.ptr = cp.data(); d.cmap.idx = nz(ci); d.cmap.val = nzd(cv);
+    d.b0 = b0.data(); d.bmap.ptr = bp.data(); d.bmap.idx = nz(bi); d.bmap.val = nzd(bv);
+    d.u0 = u0.data(); d.umap.ptr = up.data(); d.umap.idx = nz(ui); d.umap.val = nzd(uv);
+    d.o0 = D->o0; d.omap = D->omap ? D->omap : zPr.data(); d.ocmap = D->ocmap ? D->ocmap : zPc.data();
+    dsp_template *T = nullptr;
+    rc = dsp_lp_template_create(&d, &T);
+    if (rc) return rc;
+    T->col_perm = R.col_perm; T->row_perm = R.row_perm;
+    int *dx = nullptr, *dy = nullptr;
+    rc = upload(R.col_perm, &dx);
+    if (!rc) { T->dev_allocs.push_back(dx); rc = upload(R.row_perm, &dy); }
+    if (rc) { dsp_lp_template_destroy(T); return rc; }
+    T->dev_allocs.push_back(dy);
+    T->kp.xperm = dx; T->kp.yperm = dy;
+    *out = T;
+    return 0;
+}
+
+int dsp_lp_template_info(const dsp_template *T, int32_t *m, int32_t *n, int32_t *nb, int32_t *w) {
+    if (!T) { g_err = "dsp_lp_template_info: null handle"; return DSP_E_ARG; }
+    if (m) *m = T->kp.m;
+    if (n) *n = T->kp.n;
+    if (nb) *nb = T->kp.nb;
+    if (w) *w = T->kp.w;
     return 0;
 }
 

@@ -35,7 +35,7 @@ namespace stage2 {
 
 #define S2D __device__ __forceinline__
 #ifndef DSP_S2_SYNCMASK          // which of the five phase boundaries of a round carry a CTA barrier (experiments: tools/build_variants.py)
-#define DSP_S2_SYNCMASK 31
+#define DSP_S2_SYNCMASK 0       // measured: the exit vote at the top of the round alone keeps the warps in step (profiles/stage2_variants_r2.log)
 #endif
 constexpr unsigned FULL = 0xffffffffu;
 constexpr double kGapFloor2 = 1e-4;
@@ -71,8 +71,10 @@ S2D double frcp(double x) {
 #endif
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
+#if !defined(DSP_S2_RCP_NEWTON) || DSP_S2_RCP_NEWTON >= 2
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
+#endif
     return r;
 }
 S2D double dmax(double a, double b) { return a > b ? a : b; }

@@ -274,3 +274,224 @@ class TemplateBuilder:
         t = LPTemplate(self.name, A, b0, Bmap, c0, Cmap, u0, Umap, self.o0, self.omap.copy(), self.ocmap.copy(),
                        shifts.copy(), np.ones(n), list(self.cols), list(self.rows), dict(self.meta))
         return t.finalize(equilibrate=equilibrate)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def standard_form(rows, lo, hi, lb, ub, cost, c0=0.0, sense=1.0, var_names=None, row_names=None, name="lp",
+                  p0=None, dcost=None, dlo=None, dhi=None, dlb=None, dub=None, dc0=None, equilibrate=True, presolve=True):
+    """General LP -> LPTemplate (the pure, pyomo-free half of the Pyomo walker).
+
+        optimise  sense * (cost'x + c0)   s.t.   lo <= rows x <= hi,   lb <= x <= ub
+
+    ``rows`` is a list of {column: coefficient} dicts; any of lo / hi / lb / ub may be -inf / +inf (free Vars such as
+    pem.electricity -- domain Reals, unit_models/pem_electrolyzer.py:96-100 -- ranged rows, fixed Vars lb == ub).
+    Batched parameters: the LP was extracted at parameter values ``p0`` [P]; ``dcost`` [n,P], ``dlo`` / ``dhi`` [m,P],
+    ``dlb`` / ``dub`` [n,P], ``dc0`` [P] are the derivatives of the affine data with respect to them (the constraint matrix
+    may not depend on parameters: it is shared by the batch).  One parameter vector serves as cparams and rparams.
+
+    Column transformations (undone by ``model_values``):  fixed -> constant;  finite lb: x = lb + x';  only ub finite:
+    x = ub - x';  free: x = x+ - x-;  both finite: 0 <= x' <= ub - lb.  Inequality rows get a slack column, ranged rows a bounded
+    one.  ``presolve`` substitutes doubleton equalities  a x_i + b x_j = rhs  with a free / identically bounded x_i (the arcs and
+    link constraints of a Pyomo multi-period model, wind_battery_LMP.py:22-50) -- they would otherwise widen the band of A A'.
+    Returns an LPTemplate whose meta["recover"] maps template columns back to the model's variables and meta["row_of"] the
+    template row of every model row (for duals)."""
+    n = len(lb)
+    m = len(rows)
+    lb = np.asarray(lb, float).copy(); ub = np.asarray(ub, float).copy()
+    lo = np.asarray(lo, float).copy(); hi = np.asarray(hi, float).copy()
+    P = 0 if p0 is None else len(p0)
+    p0 = np.zeros(0) if p0 is None else np.asarray(p0, float)
+    Z = lambda a, shape: np.zeros(shape) if a is None else np.asarray(a, float).reshape(shape)
+    dcost, dlo, dhi, dlb, dub, dc0 = Z(dcost, (n, P)), Z(dlo, (m, P)), Z(dhi, (m, P)), Z(dlb, (n, P)), Z(dub, (n, P)), Z(dc0, (P,))
+    cvec = np.zeros(n)
+    for j, v in (cost.items() if isinstance(cost, dict) else enumerate(np.asarray(cost, float))):
+        cvec[j] = v
+    # ---- model variable j = const_j + sum_k coef * y_k in terms of working variables y (affine in params through const)
+    # working representation: every model variable is  shift_j(p) + sign_j * y_{col_j}  [- y_{col2_j}] ; presolve may alias
+    # variable i to variable j:  x_i = alpha * x_j + beta
+    alias = {}                                        # i -> (j, alpha, beta0, dbeta[P])
+    rows = [dict(r) for r in rows]
+    live_row = np.ones(m, bool)
+    if presolve:
+        use = [set() for _ in range(n)]
+        for r, row in enumerate(rows):
+            for j in row:
+                use[j].add(r)
+        changed = True
+        while changed:
+            changed = False
+            for r in range(m):
+                if not live_row[r] or lo[r] != hi[r] or len(rows[r]) != 2 or np.any(dlo[r] != dhi[r]):
+                    continue
+                (i, a), (j, b) = rows[r].items()
+                fixed = lambda k: lb[k] == ub[k] and not dlb[k].any() and not dub[k].any()
+                if fixed(i) or fixed(j):
+                    continue
+                # eliminate the one whose bounds are implied: free, or the same box after the affine map (alpha > 0, beta = 0)
+                for (e, ae), (k, ak) in (((i, a), (j, b)), ((j, b), (i, a))):
+                    alpha, beta = -ak / ae, hi[r] / ae
+                    same_box = alpha == 1.0 and beta == 0.0 and not dhi[r].any() and lb[e] == lb[k] and ub[e] == ub[k] \
+                        and not (dlb[e] - dlb[k]).any() and not (dub[e] - dub[k]).any()
+                    free = not np.isfinite(lb[e]) and not np.isfinite(ub[e])
+                    if not (free or same_box) or dcost[e].any() and (dhi[r].any()):
+                        continue
+                    # merging must stay local in time: chains of link equalities over ALL periods (nameplate_power[t] =
+                    # nameplate_power[t+1]) would collapse into one dense column and destroy the band of A A'
+                    if len((use[e] | use[k]) - {r}) > 8:
+                        continue
+                    # substitute x_e = alpha x_k + beta(p) everywhere
+                    alias[e] = (k, alpha, beta, dhi[r] / ae)
+                    live_row[r] = False
+                    for rr in list(use[e]):
+                        if rr == r or not live_row[rr]:
+                            continue
+                        coef = rows[rr].pop(e)
+                        rows[rr][k] = rows[rr].get(k, 0.0) + coef * alpha
+                        if rows[rr][k] == 0.0:
+                            del rows[rr][k]
+                        else:
+                            use[k].add(rr)
+                        lo[rr] -= coef * beta; hi[rr] -= coef * beta
+                        dlo[rr] = dlo[rr] - coef * dhi[r] / ae; dhi[rr] = dhi[rr] - coef * dhi[r] / ae
+                    c0 = c0 + cvec[e] * beta
+                    dc0 = dc0 + cvec[e] * dhi[r] / ae + dcost[e] * beta
+                    cvec[k] += cvec[e] * alpha; dcost[k] = dcost[k] + dcost[e] * alpha
+                    cvec[e] = 0.0; dcost[e] = 0.0
+                    use[e] = set()
+                    changed = True
+                    break
+    # ---- columns
+    kind = np.zeros(n, int)          # 0 fixed/const, 1 lb-shift, 2 ub-flip, 3 free split, 4 boxed, 5 alias
+    col, col2 = -np.ones(n, int), -np.ones(n, int)
+    cols_u0, cols_du, names = [], [], []
+    vn = var_names or [f"x[{j}]" for j in range(n)]
+    nc = 0
+    for j in range(n):
+        if j in alias:
+            kind[j] = 5
+            continue
+        moving = dlb[j].any() or dub[j].any()
+        if lb[j] == ub[j] and not moving:
+            kind[j] = 0
+        elif np.isfinite(lb[j]) and np.isfinite(ub[j]):
+            kind[j] = 4; col[j] = nc; nc += 1; cols_u0.append(ub[j] - lb[j]); cols_du.append(dub[j] - dlb[j]); names.append(vn[j])
+        elif np.isfinite(lb[j]):
+            kind[j] = 1; col[j] = nc; nc += 1; cols_u0.append(INF); cols_du.append(np.zeros(P)); names.append(vn[j])
+        elif np.isfinite(ub[j]):
+            kind[j] = 2; col[j] = nc; nc += 1; cols_u0.append(INF); cols_du.append(np.zeros(P)); names.append(vn[j] + ":flipped")
+        else:
+            kind[j] = 3; col[j] = nc; col2[j] = nc + 1; nc += 2
+            cols_u0 += [INF, INF]; cols_du += [np.zeros(P)] * 2; names += [vn[j] + ":pos", vn[j] + ":neg"]
+    # x_j = shift_j(p) + sgn_j * y[col_j] (- y[col2_j])
+    shift0 = np.where(kind == 2, ub, np.where((kind == 1) | (kind == 4) | (kind == 0), lb, 0.0))
+    shift0 = np.where(np.isfinite(shift0), shift0, 0.0)
+    dshift = np.where((kind == 2)[:, None], dub, np.where(((kind == 1) | (kind == 4))[:, None], dlb, 0.0))
+    sgn = np.where(kind == 2, -1.0, 1.0)
+    if np.any((np.abs(dcost).sum(1) > 0) & (np.abs(dshift).sum(1) > 0)):
+        raise ValueError("a Var whose cost AND whose bound depend on batched Params makes the objective constant quadratic in them")
+    # ---- rows
+    ri, ci, vv = [], [], []
+    b0, db, row_of = [], [], -np.ones(m, int)
+    slack_sign = []
+    mr = 0
+    for r in range(m):
+        if not live_row[r]:
+            continue
+        row = rows[r]
+        if not any(kind[j] != 0 for j in row):       # only constants left (fixed Vars): nothing to solve for in this row
+            continue
+        sh = sum(a * shift0[j] for j, a in row.items()); dsh = sum(a * dshift[j] for j, a in row.items())
+        for j, a in row.items():
+            if kind[j] == 0:
+                continue
+            ri.append(mr); ci.append(col[j]); vv.append(a * sgn[j])
+            if kind[j] == 3:
+                ri.append(mr); ci.append(col2[j]); vv.append(-a)
+        if lo[r] == hi[r] and not (dlo[r] - dhi[r]).any():
+            b0.append(hi[r] - sh); db.append(dhi[r] - dsh)
+        elif not np.isfinite(lo[r]):
+            ri.append(mr); ci.append(nc); vv.append(1.0); nc += 1
+            cols_u0.append(INF); cols_du.append(np.zeros(P)); names.append(f"slack[{r}]")
+            b0.append(hi[r] - sh); db.append(dhi[r] - dsh)
+        elif not np.isfinite(hi[r]):
+            ri.append(mr); ci.append(nc); vv.append(-1.0); nc += 1
+            cols_u0.append(INF); cols_du.append(np.zeros(P)); names.append(f"surplus[{r}]")
+            b0.append(lo[r] - sh); db.append(dlo[r] - dsh)
+        else:                                         # ranged: a x + s = hi, 0 <= s <= hi - lo
+            ri.append(mr); ci.append(nc); vv.append(1.0); nc += 1
+            cols_u0.append(hi[r] - lo[r]); cols_du.append(dhi[r] - dlo[r]); names.append(f"range[{r}]")
+            b0.append(hi[r] - sh); db.append(dhi[r] - dsh)
+        row_of[r] = mr
+        mr += 1
+    A = sp.csr_matrix((vv, (ri, ci)), shape=(mr, nc))
+    A.sum_duplicates()
+    # ---- objective: sense * (sum_j c_j(p) x_j + c0(p)),  x_j = shift_j(p) + sgn_j y  (cost or shift param-free per column)
+    c_t = np.zeros(nc); C_t = np.zeros((nc, P))
+    for j in range(n):
+        if kind[j] in (0, 5):
+            continue
+        c_t[col[j]] += sense * cvec[j] * sgn[j]; C_t[col[j]] += sense * dcost[j] * sgn[j]
+        if kind[j] == 3:
+            c_t[col2[j]] -= sense * cvec[j]; C_t[col2[j]] -= sense * dcost[j]
+    o_at_p0 = sense * (c0 + float(cvec @ shift0))
+    do = sense * (dc0 + dcost.T @ shift0 + dshift.T @ cvec)
+    b0 = np.array(b0, float); db = np.array(db, float).reshape(mr, P)
+    u0 = np.array(cols_u0, float); dU = np.array(cols_du, float).reshape(nc, P)
+    # values at p0 -> affine maps in p:  q(p) = q(p0) + dq (p - p0)
+    t = LPTemplate(name, A, b0 - db @ p0 if P else b0, sp.csr_matrix(db), c_t - C_t @ p0 if P else c_t, sp.csr_matrix(C_t),
+                   np.where(np.isfinite(u0), u0 - (dU @ p0 if P else 0.0), INF), sp.csr_matrix(np.where(np.isfinite(u0)[:, None], dU, 0.0)),
+                   o_at_p0 - float(do @ p0) if P else o_at_p0, do.copy() * 0.0, do.copy(),
+                   np.zeros(nc), np.ones(nc), names, [f"row[{i}]" for i in range(mr)],
+                   dict(kind="standard_form", sense=sense))
+    t.meta["recover"] = dict(kind=kind, col=col, col2=col2, sgn=sgn, shift0=shift0, dshift=dshift, p0=p0, alias=alias, names=list(names))
+    t.meta["row_of"] = row_of
+    t.meta["live_row"] = live_row
+    # objective constant rides on ocmap (cparams) only: omap stays zero so that cparams == rparams does not count it twice
+    return t.finalize(equilibrate=equilibrate)
+
+
+def model_values(t: LPTemplate, x, params=None):
+    """Template-space primal x [N, n] of a standard_form() template -> the model's variable values [N, n_model]."""
+    rec = t.meta["recover"]
+    x = np.atleast_2d(np.asarray(x, float))
+    N = x.shape[0]
+    pos = {nm: k for k, nm in enumerate(t.col_names)}                  # finalize() permutes columns: go through the names
+    xm = x * t.col_scale + t.col_shift
+    P = rec["p0"].size
+    dp = (np.atleast_2d(params) - rec["p0"]) if (params is not None and P) else np.zeros((N, P))
+    n = rec["kind"].size
+    out = np.zeros((N, n))
+    names = rec["names"]
+    for j in range(n):
+        k = rec["kind"][j]
+        if k == 5:
+            continue
+        v = rec["shift0"][j] + (dp @ rec["dshift"][j] if P else 0.0)
+        if k != 0:
+            v = v + rec["sgn"][j] * xm[:, pos[names[rec["col"][j]]]]
+            if k == 3:
+                v = v - xm[:, pos[names[rec["col2"][j]]]]
+        out[:, j] = v
+    done = set(j for j in range(n) if rec["kind"][j] != 5)
+    pending = dict(rec["alias"])
+    while pending:                                                      # aliases may chain
+        for e, (k, alpha, beta, dbeta) in list(pending.items()):
+            if k in done:
+                out[:, e] = alpha * out[:, k] + beta + (dp @ dbeta if P else 0.0)
+                done.add(e); del pending[e]
+    return out
+
+
+def model_duals(t: LPTemplate, y):
+    """Row duals y [N, m] of a standard_form() template -> d(objective)/d(rhs) of the model's rows [N, m_model] (0 for rows
+    presolve removed)."""
+    y = np.atleast_2d(np.asarray(y, float))
+    R = t.meta.get("row_scale")
+    pos = {nm: k for k, nm in enumerate(t.row_names)}
+    row_of = t.meta["row_of"]
+    out = np.zeros((y.shape[0], row_of.size))
+    for r, mr in enumerate(row_of):
+        if mr >= 0:
+            k = pos[f"row[{mr}]"]
+            out[:, r] = y[:, k] * (R[mr] if R is not None else 1.0) * t.meta["sense"]
+    return out

@@ -27,7 +27,7 @@ STATUS_NAMES = {OPTIMAL: "optimal", MAX_ITER: "maxIterations", NUMERICAL: "error
 
 KERNEL_AUTO, KERNEL_BAND, KERNEL_STAGE, KERNEL_STAGE_V1 = 0, 1, 2, 3
 
-EXPORTS = ["dsp_lp_template_create", "dsp_lp_template_destroy", "dsp_lp_template_set_stage_wb", "dsp_lp_default_opts", "dsp_lp_solve_batch",
+EXPORTS = ["dsp_lp_template_create", "dsp_lp_template_create_csr", "dsp_lp_analyze_csr", "dsp_lp_template_info", "dsp_lp_template_destroy", "dsp_lp_template_set_stage_wb", "dsp_lp_default_opts", "dsp_lp_solve_batch",
            "dsp_lp_solve_batch_host", "dsp_lp_launch_count", "dsp_lp_last_launch", "dsp_lp_last_error",
            "dsp_lp_version", "dsp_lp_fp64_peak_tflops"]
 
@@ -41,6 +41,16 @@ class _Desc(C.Structure):
                 ("Pc", C.c_int32), ("Pr", C.c_int32),
                 ("A_ptr", C.c_void_p), ("A_idx", C.c_void_p), ("A_val", C.c_void_p),
                 ("asm_ptr", C.c_void_p), ("asm_col", C.c_void_p), ("asm_val", C.c_void_p),
+                ("c0", C.c_void_p), ("cmap", _ParamMap),
+                ("b0", C.c_void_p), ("bmap", _ParamMap),
+                ("u0", C.c_void_p), ("umap", _ParamMap),
+                ("o0", C.c_double), ("omap", C.c_void_p), ("ocmap", C.c_void_p)]
+
+
+class _LpDesc(C.Structure):
+    """dsp_lp_desc (include/dsp_lp.h): the plain standard-form LP handed to dsp_lp_template_create_csr"""
+    _fields_ = [("m", C.c_int32), ("n", C.c_int32), ("Pc", C.c_int32), ("Pr", C.c_int32),
+                ("A_ptr", C.c_void_p), ("A_idx", C.c_void_p), ("A_val", C.c_void_p),
                 ("c0", C.c_void_p), ("cmap", _ParamMap),
                 ("b0", C.c_void_p), ("bmap", _ParamMap),
                 ("u0", C.c_void_p), ("umap", _ParamMap),
@@ -69,6 +79,12 @@ def load_library():
     lib = C.CDLL(str(_LIB_PATH))
     lib.dsp_lp_template_create.argtypes = [C.POINTER(_Desc), C.POINTER(C.c_void_p)]
     lib.dsp_lp_template_create.restype = C.c_int
+    lib.dsp_lp_template_create_csr.argtypes = [C.POINTER(_LpDesc), C.POINTER(C.c_void_p)]
+    lib.dsp_lp_template_create_csr.restype = C.c_int
+    lib.dsp_lp_analyze_csr.argtypes = [C.POINTER(_LpDesc)] + [C.POINTER(C.c_int32)] * 4 + [C.c_void_p, C.c_void_p]
+    lib.dsp_lp_analyze_csr.restype = C.c_int
+    lib.dsp_lp_template_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+    lib.dsp_lp_template_info.restype = C.c_int
     lib.dsp_lp_template_destroy.argtypes = [C.c_void_p]
     lib.dsp_lp_template_destroy.restype = None
     lib.dsp_lp_template_set_stage_wb.argtypes = [C.c_void_p, C.POINTER(_StageWB)]
@@ -124,32 +140,55 @@ def _f64(a):
 
 
 class BatchLPSolver:
-    def __init__(self, template: LPTemplate, tol=1e-9, feas_tol=1e-9, max_iter=60, step_frac=0.9995, kernel=KERNEL_AUTO, reg_primal=1e-8):
+    def __init__(self, template: LPTemplate, tol=1e-9, feas_tol=1e-9, max_iter=60, step_frac=0.9995, kernel=KERNEL_AUTO, reg_primal=1e-8,
+                 native_setup=False):
+        """native_setup=True hands the library the PLAIN standard-form LP (dsp_lp_template_create_csr): column / row ordering and
+        the band assembly list are then derived in C++ (what a C caller or the Pyomo walker uses); the default passes the
+        orderings lp_template.finalize() computed (dsp_lp_template_create).  Results are identical up to summation order."""
         self.lib = load_library()
         self.t = template
         t = template
         nb = t.nb
         A = t.A.tocsr(); A.sort_indices()
-        Cm = t.Cmap.tocsr(); Bm = t.Bmap.tocsr(); Um = t.Umap.tocsr()[:nb]
-        keep = dict(A_ptr=_i32(A.indptr), A_idx=_i32(A.indices), A_val=_f64(A.data),
-                    asm_ptr=_i32(t.asm_ptr), asm_col=_i32(t.asm_col), asm_val=_f64(t.asm_val),
-                    c0=_f64(t.c0), b0=_f64(t.b0), u0=_f64(t.u0[:nb]),
-                    cm_ptr=_i32(Cm.indptr), cm_idx=_i32(Cm.indices), cm_val=_f64(Cm.data),
-                    bm_ptr=_i32(Bm.indptr), bm_idx=_i32(Bm.indices), bm_val=_f64(Bm.data),
-                    um_ptr=_i32(Um.indptr), um_idx=_i32(Um.indices), um_val=_f64(Um.data),
-                    omap=_f64(t.omap if t.Pr else np.zeros(1)), ocmap=_f64(t.ocmap if t.Pc else np.zeros(1)))
-        p = lambda k: keep[k].ctypes.data_as(C.c_void_p)
-        d = _Desc(m=t.m, n=t.n, nb=nb, w=t.w, Pc=t.Pc, Pr=t.Pr,
-                  A_ptr=p("A_ptr"), A_idx=p("A_idx"), A_val=p("A_val"),
-                  asm_ptr=p("asm_ptr"), asm_col=p("asm_col"), asm_val=p("asm_val"),
-                  c0=p("c0"), cmap=_ParamMap(p("cm_ptr"), p("cm_idx"), p("cm_val")),
-                  b0=p("b0"), bmap=_ParamMap(p("bm_ptr"), p("bm_idx"), p("bm_val")),
-                  u0=p("u0"), umap=_ParamMap(p("um_ptr"), p("um_idx"), p("um_val")),
-                  o0=float(t.o0), omap=p("omap"), ocmap=p("ocmap"))
+        Cm = t.Cmap.tocsr(); Bm = t.Bmap.tocsr()
         h = C.c_void_p()
-        rc = self.lib.dsp_lp_template_create(C.byref(d), C.byref(h))
-        if rc != 0:
-            raise RuntimeError(f"dsp_lp_template_create failed ({rc}): {self.lib.dsp_lp_last_error().decode()}")
+        if native_setup:
+            Um = t.Umap.tocsr()
+            keep = dict(A_ptr=_i32(A.indptr), A_idx=_i32(A.indices), A_val=_f64(A.data),
+                        c0=_f64(t.c0), b0=_f64(t.b0), u0=_f64(np.where(np.isfinite(t.u0), t.u0, 1e300)),
+                        cm_ptr=_i32(Cm.indptr), cm_idx=_i32(Cm.indices), cm_val=_f64(Cm.data),
+                        bm_ptr=_i32(Bm.indptr), bm_idx=_i32(Bm.indices), bm_val=_f64(Bm.data),
+                        um_ptr=_i32(Um.indptr), um_idx=_i32(Um.indices), um_val=_f64(Um.data),
+                        omap=_f64(t.omap if t.Pr else np.zeros(1)), ocmap=_f64(t.ocmap if t.Pc else np.zeros(1)))
+            p = lambda k: keep[k].ctypes.data_as(C.c_void_p)
+            d = _LpDesc(m=t.m, n=t.n, Pc=t.Pc, Pr=t.Pr, A_ptr=p("A_ptr"), A_idx=p("A_idx"), A_val=p("A_val"),
+                        c0=p("c0"), cmap=_ParamMap(p("cm_ptr"), p("cm_idx"), p("cm_val")),
+                        b0=p("b0"), bmap=_ParamMap(p("bm_ptr"), p("bm_idx"), p("bm_val")),
+                        u0=p("u0"), umap=_ParamMap(p("um_ptr"), p("um_idx"), p("um_val")),
+                        o0=float(t.o0), omap=p("omap"), ocmap=p("ocmap"))
+            rc = self.lib.dsp_lp_template_create_csr(C.byref(d), C.byref(h))
+            if rc != 0:
+                raise RuntimeError(f"dsp_lp_template_create_csr failed ({rc}): {self.lib.dsp_lp_last_error().decode()}")
+        else:
+            Um = t.Umap.tocsr()[:nb]
+            keep = dict(A_ptr=_i32(A.indptr), A_idx=_i32(A.indices), A_val=_f64(A.data),
+                        asm_ptr=_i32(t.asm_ptr), asm_col=_i32(t.asm_col), asm_val=_f64(t.asm_val),
+                        c0=_f64(t.c0), b0=_f64(t.b0), u0=_f64(t.u0[:nb]),
+                        cm_ptr=_i32(Cm.indptr), cm_idx=_i32(Cm.indices), cm_val=_f64(Cm.data),
+                        bm_ptr=_i32(Bm.indptr), bm_idx=_i32(Bm.indices), bm_val=_f64(Bm.data),
+                        um_ptr=_i32(Um.indptr), um_idx=_i32(Um.indices), um_val=_f64(Um.data),
+                        omap=_f64(t.omap if t.Pr else np.zeros(1)), ocmap=_f64(t.ocmap if t.Pc else np.zeros(1)))
+            p = lambda k: keep[k].ctypes.data_as(C.c_void_p)
+            d = _Desc(m=t.m, n=t.n, nb=nb, w=t.w, Pc=t.Pc, Pr=t.Pr,
+                      A_ptr=p("A_ptr"), A_idx=p("A_idx"), A_val=p("A_val"),
+                      asm_ptr=p("asm_ptr"), asm_col=p("asm_col"), asm_val=p("asm_val"),
+                      c0=p("c0"), cmap=_ParamMap(p("cm_ptr"), p("cm_idx"), p("cm_val")),
+                      b0=p("b0"), bmap=_ParamMap(p("bm_ptr"), p("bm_idx"), p("bm_val")),
+                      u0=p("u0"), umap=_ParamMap(p("um_ptr"), p("um_idx"), p("um_val")),
+                      o0=float(t.o0), omap=p("omap"), ocmap=p("ocmap"))
+            rc = self.lib.dsp_lp_template_create(C.byref(d), C.byref(h))
+            if rc != 0:
+                raise RuntimeError(f"dsp_lp_template_create failed ({rc}): {self.lib.dsp_lp_last_error().decode()}")
         self.handle = h
         self.opts = _Opts()
         self.lib.dsp_lp_default_opts(C.byref(self.opts))

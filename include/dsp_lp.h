@@ -26,7 +26,7 @@
  * lower band of M = A*diag(d)*A':  M[i][i-k] = sum_{p in asm_ptr[i*(w+1)+k] ..} asm_val[p]*d[asm_col[p]].
  * dispatches_b200/lp_template.py computes all of it.
  *
- * Size limits: half bandwidth of A*A' <= 16 (padded to 1,2,4,8,16); any m, n -- the per-LP work region lives in shared
+ * Size limits: half bandwidth of A*A' <= 32 (padded to 1,2,4,8,16,32); any m, n -- the per-LP work region lives in shared
  * memory when it fits (up to ~27 000 doubles) and in a device workspace owned by the template handle otherwise.
  *
  * All pointers in dsp_lp_solve_batch are DEVICE pointers, the call is stream-ordered and does not
@@ -104,6 +104,25 @@ enum { DSP_E_ARG = -1, DSP_E_CUDA = -2, DSP_E_SMEM = -3 };
 /* Replaces: the per-LP model hand-over inside SolverFactory(..).solve(m) (Pyomo LP/NL writer), done once. */
 int dsp_lp_template_create(const dsp_template_desc *desc, dsp_template **out);
 void dsp_lp_template_destroy(dsp_template *t);
+
+/* The same hand-over from a PLAIN standard-form LP: rows in any order, columns in any order, an upper bound >= 1e300 (or
+ * +inf) marks an unbounded column (its umap row must be empty).  The library derives what dsp_template_desc asks of its caller
+ * -- bounded columns first, a bandwidth-reducing (reverse Cuthill-McKee vs natural) row order of A A', the band assembly list --
+ * and x / y of dsp_lp_solve_batch come back in the CALLER's column / row order.  This is the entry point a C binding or the
+ * Pyomo walker uses; dsp_lp_analyze_csr is its host-only symbolic part (no CUDA call). */
+typedef struct {
+    int32_t m, n;                  /* rows of A x = b (inequalities carry the caller's slack columns), columns */
+    int32_t Pc, Pr;
+    const int32_t *A_ptr, *A_idx;  const double *A_val;        /* CSR, m rows                               */
+    const double *c0;  dsp_param_map cmap;                     /* n rows over cparams (c0 may be NULL = 0)   */
+    const double *b0;  dsp_param_map bmap;                     /* m rows over rparams (b0 may be NULL = 0)   */
+    const double *u0;  dsp_param_map umap;                     /* n rows over rparams; u0[j] >= 1e300: none  */
+    double o0; const double *omap /*[Pr] or NULL*/; const double *ocmap /*[Pc] or NULL*/;
+} dsp_lp_desc;
+int dsp_lp_template_create_csr(const dsp_lp_desc *desc, dsp_template **out);
+int dsp_lp_analyze_csr(const dsp_lp_desc *desc, int32_t *nb, int32_t *w, int32_t *w_natural, int32_t *w_rcm,
+                       int32_t *col_perm /*[n] or NULL*/, int32_t *row_perm /*[m] or NULL*/);
+int dsp_lp_template_info(const dsp_template *t, int32_t *m, int32_t *n, int32_t *nb, int32_t *w);
 
 /* Optional: registers the stage structure of a wind+battery template (see dsp_stage_wb_desc). */
 int dsp_lp_template_set_stage_wb(dsp_template *t, const dsp_stage_wb_desc *d);

@@ -3,12 +3,11 @@ import subprocess, sys, concurrent.futures as cf
 sys.path.insert(0, ".")
 from dispatches_b200.csrc import build as B
 VARIANTS = {
-    # generation-2 stage kernel: which phase boundaries of an IPM round carry a CTA barrier (bit k = boundary k of 5)
-    "s2_sync31": [],
-    "s2_sync21": ["-DDSP_S2_SYNCMASK=21"],
-    "s2_sync5": ["-DDSP_S2_SYNCMASK=5"],
-    "s2_sync1": ["-DDSP_S2_SYNCMASK=1"],
-    "s2_sync0": ["-DDSP_S2_SYNCMASK=0"],           # only the exit vote at the top of the round
+    "s2_base": [],
+    "s2_rcp1": ["-DDSP_S2_RCP_NEWTON=1"],             # one Newton step after the reciprocal seed instead of two
+    "s2_warps12": ["-DDSP_S2_WARPS=12"],              # 170-register cap; run with DSP_STAGE2_GEOM=16,2 (two periods per lane)
+    "s2_warps10": ["-DDSP_S2_WARPS=10"],              # 204-register cap
+    "s2_sync31": ["-DDSP_S2_SYNCMASK=31"],
 }
 out = B.ROOT / "build" / "variants"
 out.mkdir(parents=True, exist_ok=True)

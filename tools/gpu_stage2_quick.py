@@ -17,9 +17,9 @@ def timed(sol, cp, rp, reps=9):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); sol.solve(cp, rp, out=o); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return o, float(np.median(ts))
-a, ms = timed(v2, cp, rpt); a5, ms5 = timed(v2, cp5, rp5, 3)
+a, ms = timed(v2, cp, rpt); la = S.last_launch(); a5, ms5 = timed(v2, cp5, rp5, 3)
 b = v1.solve(cp, rpt); torch.cuda.synchronize()
 rel = float(((a.obj - b.obj).abs() / b.obj.abs().clamp(min=1)).max())
 print("%s: C2 %.3f ms (nonopt %d, iters %.2f, rel vs v1 %.1e)  C5/128k %.3f ms (nonopt %d) %s" % (
     os.path.basename(os.environ.get("DSP_LP_LIB", "default")), ms, int((a.status != 0).sum()), float(a.iters.float().mean()), rel, ms5,
-    int((a5.status != 0).sum()), S.last_launch()), flush=True)
+    int((a5.status != 0).sum()), la), flush=True)
