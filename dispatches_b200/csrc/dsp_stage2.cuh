@@ -318,6 +318,14 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
             }
         }
         if (cta_all<CTA_SYNC>(mode == 3)) break;
+        if (__all_sync(FULL, mode == 3)) {
+            // this warp is out of work while others of its CTA still iterate: it must not compete for their issue slots --
+            // it only keeps the CTA's barriers of the round balanced and waits at the next exit vote
+#pragma unroll
+            for (int b = 0; b < 5; ++b)
+                if (DSP_S2_SYNCMASK & (1 << b)) cta_sync<CTA_SYNC>();
+            continue;
+        }
 
         // =========================================================================================== neighbours of the lane's block
         const double xs_left = gup1<L>(pr[P - 1].xs, gl), xe_left = gup1<L>(pr[P - 1].xe, gl);

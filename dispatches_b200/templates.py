@@ -286,6 +286,56 @@ def nuclear(T: int = 48, np_capacity=500.0, pem_capacity=100.0, tank_capacity=50
     return B.build(equilibrate=True)          # kW, mol/s and mol columns differ by 1e4: equilibrate (fewer iterations)
 
 
+def nuclear_report(T: int, pem_capex=400.0, demand=400.0 * 20, vom_pem=0.0, plant_life=30, tax_rate=0.2, discount_rate=0.08,
+                   np_mw=400.0) -> LPTemplate:
+    """The report's price-taker LP with storage tank and hydrogen turbine (nuclear_case/report/price_taker_analysis.py:116-322):
+    build_ne_flowsheet rows (:143-170) reduced to one tank balance per hour --
+        np_to_grid = 400 - e,  h2_production = 20 e,  h2_turbine_power = 0.0125 tb,  net_power = 400 - e + 0.0125 tb,
+        H[t] - H[t-1] = 20 e[t] - u[t] - tb[t]       (link :175-178, tank_holdup_previous[1] = 0 :377)
+    columns e (np_to_electrolyzer <= pem_capacity, :199-203), u (h2_to_pipeline <= demand, :219-220), tb (h2_to_turbine,
+    turbine power <= h2_turbine_capacity :209-213), H (tank_holdup <= tank_capacity :204-208).  Objective = -(net_profit -
+    capex / cf) of append_* (:239-322; the reference maximises).  The sweep of run_exhaustive_enumeration fixes the three
+    capacities (:377-403): they are batch parameters here.
+    cparams = [lmp (T), h2_price];  rparams = [pem_capacity MW, tank_capacity kg, h2_turbine_capacity MW]."""
+    ih2 = T
+    iPem, iTank, iTurb = 0, 1, 2
+    k = 1.0 - tax_rate
+    cf = (1.0 - (1.0 + discount_rate) ** (-plant_life)) / discount_rate
+    B = TemplateBuilder(f"nuclear_report_T{T}", Pc=T + 1, Pr=3)
+    e, u, tb, H = {}, {}, {}, {}
+    for t in range(T):
+        p = f"period[{t + 1}].fs."
+        e[t] = B.var(p + "np_to_electrolyzer", ub=(0.0, {iPem: 1.0}))
+        u[t] = B.var(p + "h2_to_pipeline", ub=demand)
+        tb[t] = B.var(p + "h2_to_turbine", ub=(0.0, {iTurb: 1.0 / 0.0125}))
+        H[t] = B.var(p + "tank_holdup", ub=(0.0, {iTank: 1.0}))
+        # cash flow (:239-254): h2_price u + lmp net_power - (vom e + 4.25 turbine_power + 2.3 np_power); minimise -(1 - tax) * cash
+        B.cost(e[t], (k * vom_pem, {t: k}))                     # -k lmp (400 - e + ...)  ->  + k lmp e
+        B.cost(tb[t], (k * 4.25 * 0.0125, {t: -k * 0.0125}))
+        B.cost(u[t], (0.0, {ih2: -k}))
+        B.ocmap[t] += -k * np_mw
+        B.obj_const(k * 2.3 * np_mw)
+    for t in range(T):
+        row = {H[t]: 1.0, e[t]: -20.0, u[t]: 1.0, tb[t]: 1.0}
+        if t > 0:
+            row[H[t - 1]] = -1.0
+        B.eq(f"tank_mass_balance[{t + 1}]", row)
+    # NPV pieces (:274-308): capex = 1000 capex_pem pem + 29*33.3 tank + 1000*947 turbine; fom = 1000 fom_pem pem + 7000 turbine + 120e3*400
+    # objective = -(dep + k (cash - fom - dep) - capex / cf),  dep = capex / life
+    fom_pem = 0.03 * pem_capex
+    capex_coef = {iPem: pem_capex * 1000.0, iTank: 29.0 * 33.3, iTurb: 947.0 * 1000.0}
+    fom_coef = {iPem: 1000.0 * fom_pem, iTurb: 1000.0 * 7.0}
+    lin = {}
+    for i, cc in capex_coef.items():
+        lin[i] = lin.get(i, 0.0) - (cc / plant_life) * (1.0 - k) + cc / cf
+    for i, fc in fom_coef.items():
+        lin[i] = lin.get(i, 0.0) + k * fc
+    B.obj_const((k * 120.0 * 1000.0 * np_mw, lin))
+    B.meta.update(kind="nuclear_report", T=T, capex_coef=capex_coef, fom_coef=fom_coef, fom_const=120.0 * 1000.0 * np_mw, k=k, cf=cf,
+                  plant_life=plant_life, np_mw=np_mw)
+    return B.build(equilibrate=True)
+
+
 # ---------------------------------------------------------------------------------------------
 FOSSIL = dict(p_lo=283.0, p_hi=436.0, pprev_lo=284.0, pprev_hi=466.0, hx_lo=10.0, hx_hi=200.0, ramp=60.0,
               salt_total=6739292.0, hot_init=75000.0 + 1103053.48, pprev0=447.66,

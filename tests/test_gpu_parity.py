@@ -426,6 +426,30 @@ def test_c2_full_batch_objective_parity_1e6(wb):
     assert rel_err(r.obj, ref).max() < REL
 
 
+def test_nuclear_report_lp_with_tank_and_turbine_full_year(tmp_path):
+    """price_taker_analysis.py:116-222 with tank_capacity / h2_turbine_capacity > 0: the hours couple through the tank holdup, so
+    the 8784-period LPs of the enumeration (:353-425) run on the CUDA solver (band kernel, workspace mode) in one batch;
+    net NPV against HiGHS on the raw oracle LP, schedule CSVs with the columns of _write_results (:325-350)."""
+    import pandas as pd
+    from dispatches_b200 import run_pricetaker as RP
+    lmp = SC.pool()["nuc_report_lmp_rt"]
+    assert lmp.size == 8784
+    kw = dict(tank_capacity=50000.0, turbine_capacity=40.0, demand=2000.0)
+    res = RP.run_exhaustive_enumeration(lmp, pem_capex=400.0, h2_prices=(1.0, 2.0), pem_fractions=(0.1, 0.3),
+                                        schedule_csv_dir=tmp_path, **kw)
+    assert all(v == "optimal" for v in res["solver_stat"].values())
+    for key, hp, pc in (("00", 1.0, 0.1), ("11", 2.0, 0.3)):
+        ref, _ = H.solve(L.nuclear_report_raw(lmp, hp, pc * 400.0, pem_capex=400.0, tank_cap=kw["tank_capacity"],
+                                              turbine_cap=kw["turbine_capacity"], demand=kw["demand"]))
+        assert res["net_npv"][key] == pytest.approx(-ref / 1e6, rel=1e-6)
+    df = pd.read_csv(tmp_path / "results_11_schedule.csv", index_col=0)
+    assert list(df.columns) == ["LMP [$/MWh]", "np_to_grid", "np_to_electrolyzer", "tank_holdup_previous", "tank_holdup", "h2_to_pipeline",
+                                "h2_to_turbine", "h2_turbine_power", "h2_revenue", "electricity_revenue", "vom", "net_cash_inflow"]
+    assert len(df) == 8784 and df["tank_holdup"].max() > 1000.0 and df["tank_holdup"].max() <= 50000.0 * (1 + 1e-6)
+    bal = df["tank_holdup"] - df["tank_holdup_previous"] - 20.0 * df["np_to_electrolyzer"] + df["h2_to_pipeline"] + df["h2_to_turbine"]
+    assert bal.abs().max() < 1e-3 * 8000.0 * 1e-3
+
+
 def test_long_horizon_wind_battery_quarter_year():
     """run_pricetaker_wind_battery.run_design's kind of LP (the reference uses n_time_points = 8736): a 2184-period
     wind+battery LP against the oracle; the throughput column grows with the horizon (scale-invariant proximal term)."""

@@ -45,3 +45,19 @@ def test_rparams_layout_matches_the_stage_descriptor():
     g0 = t.col_names.index("blk[0].fs.splitter.grid_elec[0]")
     assert c[g0] == pytest.approx(st["k_rev"])                              # cost of g_t = k_rev * lmp_t
     assert st["col_idx"][0, 0] == g0 and st["col_idx"][23, 3] == -1         # s[T-1] presolved away
+
+
+def test_simulation_data_files_parse_like_the_reference_reader(tmp_path):
+    """write_simulation_data -> the parsing steps of Simulation_Data._read_data_to_array / read_data_to_dict (:138-220)"""
+    import re
+    import pandas as pd
+    from dispatches_b200 import run_pricetaker as RP
+    rng = np.random.default_rng(0)
+    disp = rng.uniform(0, 200, (4, 48)); inp = rng.uniform(0, 1, (4, 3))
+    out = RP.write_simulation_data(disp, inp, tmp_path / "sim.csv", tmp_path / "inputs.h5", ["pmax", "battery_ratio", "threshold"])
+    df = pd.read_csv(out["dispatch_csv"], nrows=3)                            # the reader: nrows = num_sims
+    run_index = df.iloc[:, 0].to_numpy(dtype=str)
+    index = [int(re.split(r"_|\.", r)[1]) for r in run_index]
+    assert index == [0, 1, 2] and np.allclose(df.iloc[:, 1:].to_numpy(dtype=float), disp[:3])
+    dfi = pd.read_hdf(out["input_file"]) if out["input_format"] == "hdf" else pd.read_csv(out["input_file"])
+    assert np.allclose(dfi.iloc[index, list(range(1, dfi.shape[1]))].to_numpy(), inp[:3])

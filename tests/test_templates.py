@@ -131,6 +131,14 @@ def test_nuclear_report_enumeration_presolve_equals_the_full_lp():
             obj, x = H.solve(L.nuclear_report_raw(lmp, hp, pc * 400.0, pem_capex=400.0))
             assert res["net_npv"][f"{i1}{i2}"] == pytest.approx(-obj / 1e6, rel=1e-9)
     assert 0.0 <= res["pem_cap_factor"]["11"] <= 1.0 and res["solver_stat"]["00"] == "optimal"
+    # schedule files in the format of _write_results (price_taker_analysis.py:325-350)
+    import tempfile, pandas as pd
+    with tempfile.TemporaryDirectory() as td:
+        RP.run_exhaustive_enumeration(lmp, pem_capex=400.0, h2_prices=(1.5,), pem_fractions=(0.5,), schedule_csv_dir=td)
+        df = pd.read_csv(f"{td}/results_00_schedule.csv", index_col=0)
+        assert list(df.columns)[:3] == ["LMP [$/MWh]", "np_to_grid", "np_to_electrolyzer"] and len(df) == lmp.size
+        assert np.allclose(df["net_cash_inflow"], df["h2_revenue"] + df["electricity_revenue"] - df["vom"])
+        assert res["h2_rev"]["11"] * 1e6 == pytest.approx(df["h2_revenue"].sum(), rel=1e-12)
 
 
 def test_design_free_wind_matches_raw_oracle():
@@ -149,3 +157,15 @@ def test_design_free_wind_matches_raw_oracle():
             assert r.status == 0, r.message
             ref, _ = H.solve(L.wind_battery_raw(lmp[k] * scale, cf, W, P, design_opt=True, extant_wind=False))
             assert r.fun + kk == pytest.approx(ref, rel=1e-9, abs=1e-6)
+
+
+@pytest.mark.parametrize("tank,turb,demand", [(30000.0, 0.0, 3000.0), (50000.0, 40.0, 2000.0), (0.0, 25.0, 8000.0)])
+def test_nuclear_report_with_tank_and_turbine_matches_raw_oracle(tank, turb, demand):
+    """the report LP with a storage tank / hydrogen turbine (price_taker_analysis.py:116-222): reduced template == raw oracle LP"""
+    from test_double_loop import solve_template
+    lmp = SC.pool()["nuc_report_lmp_rt"][3000:3168]
+    t = TP.nuclear_report(168, pem_capex=400.0, demand=demand)
+    for hp, pem in ((0.75, 40.0), (2.0, 200.0), (1.25, 120.0)):
+        obj, x = solve_template(t, np.r_[lmp, hp], np.array([pem, tank, turb]))
+        ref, xr = H.solve(L.nuclear_report_raw(lmp, hp, pem, pem_capex=400.0, tank_cap=tank, turbine_cap=turb, demand=demand))
+        assert obj == pytest.approx(ref, rel=1e-10)
