@@ -79,3 +79,22 @@ def test_forced_rebuild_from_source():
     t0 = time.time()
     lib = build.build(force=True)
     assert lib.exists() and lib.stat().st_mtime >= t0 - 1.0
+
+
+def build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    from dispatches_b200.csrc import build
+    lib = build.build()
+    exe = tmp_path / "c_abi_example"
+    cmd = [shutil.which("gcc") or "gcc", "-std=c99", "-O1", "-Wall", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "c_abi_example.c"),
+           f"-L{lib.parent}", "-ldsp_lp", f"-Wl,-rpath,{lib.parent}", "-lm", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_the_c_abi_compiles_and_links_from_plain_c(tmp_path):
+    """include/dsp_lp.h is C99-clean and a C program links against libdsp_lp.so with nothing but the header"""
+    exe = build_c_example(tmp_path)
+    assert exe.exists()

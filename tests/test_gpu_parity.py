@@ -105,7 +105,8 @@ def test_stage_and_band_kernels_agree(wb):
     lmp, cf, W, P = SC.c2(2000)
     rp = TP.wind_battery_rparams(24, cf, W, P)[0]
     a = sol.solve_host(lmp, rp, want_x=True, want_y=True)
-    assert S.last_launch()["problems_per_cta"] == 4            # generation 2: four LPs per warp at T = 24
+    ll = S.last_launch()
+    assert ll["problems_per_cta"] == 4 * (ll["block"] // 32)  # generation 2: four LPs per warp at T = 24
     b = band.solve_host(lmp, rp, want_x=True, want_y=True)
     assert S.last_launch()["smem_bytes"] > 40000
     c = v1.solve_host(lmp, rp, want_x=True, want_y=True)
@@ -448,6 +449,40 @@ def test_nuclear_report_lp_with_tank_and_turbine_full_year(tmp_path):
     assert len(df) == 8784 and df["tank_holdup"].max() > 1000.0 and df["tank_holdup"].max() <= 50000.0 * (1 + 1e-6)
     bal = df["tank_holdup"] - df["tank_holdup_previous"] - 20.0 * df["np_to_electrolyzer"] + df["h2_to_pipeline"] + df["h2_to_turbine"]
     assert bal.abs().max() < 1e-3 * 8000.0 * 1e-3
+
+
+@pytest.mark.parametrize("kind", ["wind_battery", "nuclear", "wind_battery_pem", "bidder_da"])
+def test_native_setup_from_plain_csr(kind):
+    """dsp_lp_template_create_csr: the library derives column order, row order (RCM vs natural) and the band assembly list itself
+    from the plain standard-form LP; results (incl. x and y in the caller's order) equal the Python-prepared descriptor's."""
+    if kind == "wind_battery":
+        t = TP.wind_battery(24); lmp, cf, W, P = SC.c2(96); cp = lmp; rp = TP.wind_battery_rparams(24, cf, W, P)[0]
+    elif kind == "nuclear":
+        t = TP.nuclear(48); cp = SC.c3(96); rp = None
+    elif kind == "wind_battery_pem":
+        t = TP.wind_battery_pem(24); lmp, cf, W, P = SC.c2(96)
+        cp = np.concatenate([lmp, np.full((96, 1), 2.5)], axis=1); rp = TP.wind_battery_rparams(24, cf, W, 150.0, pem_mw=200.0)[0]
+    else:
+        from test_double_loop import CF, G
+        t = TP.wind_battery_operation(48, "bidder_da")
+        rng = np.random.default_rng(0)
+        da = rng.uniform(5, 80, (96, 48)); rt = rng.uniform(5, 80, (96, 48))
+        cp = np.concatenate([da, rt, np.full((96, 1), 1e3)], axis=1)
+        rp = TP.wind_battery_operation_rparams(48, np.tile(CF, (96, 1)), 200.0, 25.0, 100.0)
+    a = S.BatchLPSolver(t, kernel=S.KERNEL_BAND).solve_host(cp, rp, want_x=True, want_y=True)
+    b = S.BatchLPSolver(t, kernel=S.KERNEL_BAND, native_setup=True).solve_host(cp, rp, want_x=True, want_y=True)
+    assert (a.status == S.OPTIMAL).all() and (b.status == S.OPTIMAL).all()
+    assert rel_err(b.obj, a.obj).max() < 1e-8
+    scale = max(1.0, np.abs(a.x).max())
+    assert np.abs(a.x @ t.A.T - b.x @ t.A.T).max() <= 1e-6 * scale          # same feasible point up to the optimal face
+
+
+def test_the_c_abi_from_plain_c(tmp_path):
+    """a C program (tests/c_abi_example.c) creates a template from plain CSR, solves a batch, reads x"""
+    import subprocess
+    from test_cabi import build_c_example
+    r = subprocess.run([str(build_c_example(tmp_path))], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "C ABI OK" in r.stdout, r.stdout + r.stderr
 
 
 def test_long_horizon_wind_battery_quarter_year():
