@@ -581,6 +581,20 @@ __global__ void __launch_bounds__(32 * kStage2Warps, 1) dsp_ipm_stage2_wb_kernel
     stage2::warp_body<L, P, SYNC>(Q, s2_smem + (threadIdx.x >> 5) * stage2::SmemDoubles<P>::value, threadIdx.x & 31);
 }
 
+}  // namespace
+
+#include "dsp_stage_chain1.cuh"
+
+namespace {
+// descriptor-driven stage kernel of the single-storage-chain family (dsp_stage_chain1.cuh): same CTA shape as stage2
+template <int L, int P, int NF>
+__global__ void __launch_bounds__(32 * kStage2Warps, 1) dsp_ipm_stage_chain1_kernel(const chain1::Params Q) {
+    extern __shared__ __align__(16) double s2_smem[];
+    chain1::warp_body<L, P, NF, true>(Q, s2_smem + (threadIdx.x >> 5) * chain1::Smem<NF, P>::doubles_per_warp, threadIdx.x & 31);
+}
+inline int chain1_lanes(int T) { return T <= 12 ? 4 : T <= 24 ? 8 : T <= 48 ? 16 : 32; }
+constexpr int kChain1MaxT = 96;
+
 struct Stage2Geom { int L, P; };
 inline Stage2Geom stage2_geometry(int T) {
     if (const char *e = getenv("DSP_STAGE2_GEOM")) {       // experiments only: "L,P"
@@ -646,6 +660,10 @@ struct dsp_template {
     mutable size_t ws_bytes;
     stagewb::StageParams sp;
     int stage_blocks_per_sm;
+    bool has_chain1;               // descriptor-driven single-storage-chain stage kernel registered
+    int c1_T, c1_NF;
+    const int *c1_col_idx, *c1_row_idx;
+    const double *c1_coef, *c1_coef_next;
     int stage2_blocks_per_sm;      // generation-2 stage kernel: CTAs (= warps) per SM for this template's (L, P)
     int device;
     int sm_count;
@@ -813,7 +831,7 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     } guard{T};
     memset(&T->kp, 0, sizeof(KParams));
     T->cap_N = 0; T->cap_x = T->cap_y = false; T->cap_rp_rows = 0;
-    T->has_stage = false; T->stage_blocks_per_sm = 0; T->stage2_blocks_per_sm = 0; T->ws = nullptr; T->ws_bytes = 0;
+    T->has_stage = false; T->has_chain1 = false; T->stage_blocks_per_sm = 0; T->stage2_blocks_per_sm = 0; T->ws = nullptr; T->ws_bytes = 0;
     T->h_cp = T->h_rp = T->h_obj = T->h_x = T->h_y = nullptr; T->h_status = T->h_iters = nullptr;
     T->d_cp = T->d_rp = T->d_obj = T->d_x = T->d_y = nullptr; T->d_status = T->d_iters = nullptr;
     T->stream = nullptr; T->stream2 = nullptr;
@@ -928,6 +946,46 @@ int dsp_lp_template_set_stage_wb(dsp_template *T, const dsp_stage_wb_desc *d) {
         T->stage2_blocks_per_sm = 1;
     }
     T->has_stage = true;
+    return 0;
+}
+
+int dsp_lp_template_set_stage_chain1(dsp_template *T, const dsp_stage_chain1_desc *d) {
+    if (!T || !d || d->T < 1 || d->T > kChain1MaxT || d->NF < 2 || d->NF > 3) {
+        g_err = "dsp_lp_template_set_stage_chain1: need 1 <= T <= 96 and NF = 2 or 3 (pad absent flows with col_idx = -1)";
+        return DSP_E_ARG;
+    }
+    if (d->T != T->kp.m) { g_err = "dsp_lp_template_set_stage_chain1: one row per period expected (T == m)"; return DSP_E_ARG; }
+    const int NC = d->NF + 1;
+    std::vector<int> ci(d->col_idx, d->col_idx + (size_t)d->T * NC), ri(d->row_idx, d->row_idx + d->T);
+    std::vector<char> seen(T->kp.n, 0);
+    for (int v : ci) {
+        if (v < -1 || v >= T->kp.n) { g_err = "chain1: col_idx out of range"; return DSP_E_ARG; }
+        if (v >= 0) { if (seen[v]) { g_err = "chain1: a column is listed twice"; return DSP_E_ARG; } seen[v] = 1; }
+    }
+    for (int j = 0; j < T->kp.n; ++j) if (!seen[j]) { g_err = "chain1: every template column must be listed"; return DSP_E_ARG; }
+    for (int v : ri) if (v < 0 || v >= T->kp.m) { g_err = "chain1: row_idx out of range"; return DSP_E_ARG; }
+    // internal (kernel) indices: templates created from plain CSR carry a caller->internal permutation
+    std::vector<int> cpos(T->kp.n), rpos(T->kp.m);
+    for (int k = 0; k < T->kp.n; ++k) cpos[T->col_perm.empty() ? k : T->col_perm[k]] = k;
+    for (int k = 0; k < T->kp.m; ++k) rpos[T->row_perm.empty() ? k : T->row_perm[k]] = k;
+    for (int &v : ci) if (v >= 0) v = cpos[v];
+    for (int &v : ri) v = rpos[v];
+    std::vector<double> cf(d->coef, d->coef + (size_t)d->T * NC), cn(d->coef_next, d->coef_next + d->T);
+    int *dci, *dri; double *dcf, *dcn;
+    int rc = upload(ci, &dci); if (rc) return rc; T->dev_allocs.push_back(dci);
+    rc = upload(ri, &dri); if (rc) return rc; T->dev_allocs.push_back(dri);
+    rc = upload(cf, &dcf); if (rc) return rc; T->dev_allocs.push_back(dcf);
+    rc = upload(cn, &dcn); if (rc) return rc; T->dev_allocs.push_back(dcn);
+    T->c1_T = d->T; T->c1_NF = d->NF;
+    T->c1_col_idx = dci; T->c1_row_idx = dri; T->c1_coef = dcf; T->c1_coef_next = dcn;
+    const int L = chain1_lanes(d->T);
+    const size_t smem = (size_t)(T->c1_NF == 2 ? chain1::Smem<2, 3>::doubles_per_warp : chain1::Smem<3, 3>::doubles_per_warp) * 8 * kStage2Warps;
+#define C1_ATTR(l, nf) do { CK(cudaFuncSetAttribute(dsp_ipm_stage_chain1_kernel<l, 3, nf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                            CK(cudaFuncSetAttribute(dsp_ipm_stage_chain1_kernel<l, 3, nf>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); } while (0)
+    if (T->c1_NF == 2) { if (L == 4) C1_ATTR(4, 2); else if (L == 8) C1_ATTR(8, 2); else if (L == 16) C1_ATTR(16, 2); else C1_ATTR(32, 2); }
+    else { if (L == 4) C1_ATTR(4, 3); else if (L == 8) C1_ATTR(8, 3); else if (L == 16) C1_ATTR(16, 3); else C1_ATTR(32, 3); }
+#undef C1_ATTR
+    T->has_chain1 = true;
     return 0;
 }
 
@@ -1054,6 +1112,34 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         std::lock_guard<std::mutex> lk(g_mu);
         g_launches++;
         g_last_grid = (int)blocks; g_last_block = wpb * 32; g_last_smem = 0; g_last_ppc = wpb;
+        return 0;
+    }
+    if (T->has_chain1 && (o.kernel == DSP_KERNEL_AUTO || o.kernel == DSP_KERNEL_STAGE)) {
+        const int L = chain1_lanes(T->c1_T), per_warp = 32 / L, NF = T->c1_NF;
+        int wmax = kStage2Warps;
+        if (const char *e = getenv("DSP_STAGE2_WARPS")) wmax = std::min(kStage2Warps, std::max(1, atoi(e)));
+        const long long warps_needed = (N + per_warp - 1) / per_warp;
+        const long long blocks = std::max<long long>(1, std::min<long long>(T->sm_count, warps_needed));
+        const int wpb = (int)std::min<long long>(wmax, (warps_needed + blocks - 1) / blocks);
+        const size_t smem = (size_t)(NF == 2 ? chain1::Smem<2, 3>::doubles_per_warp : chain1::Smem<3, 3>::doubles_per_warp) * 8 * wpb;
+        chain1::Params Q;
+        Q.N = N; Q.cparams = cparams; Q.rparams = rparams; Q.rstride = rparams_stride; Q.Pc = K.Pc; Q.Pr = K.Pr;
+        Q.omap = K.omap; Q.ocmap = K.ocmap; Q.o0 = K.o0;
+        Q.tol = o.tol; Q.feas_tol = o.feas_tol; Q.step_frac = o.step_frac; Q.reg = o.reg_primal; Q.max_iter = o.max_iter;
+        Q.obj = obj; Q.x_out = x; Q.y_out = y; Q.status = status; Q.iters = iters; Q.n = K.n; Q.m = K.m; Q.nb = K.nb; Q.ticket = ticket;
+        Q.c0 = K.c0; Q.b0 = K.b0; Q.u0 = K.u0; Q.cm_ptr = K.cm_ptr; Q.cm_idx = K.cm_idx; Q.cm_val = K.cm_val;
+        Q.bm_ptr = K.bm_ptr; Q.bm_idx = K.bm_idx; Q.bm_val = K.bm_val; Q.um_ptr = K.um_ptr; Q.um_idx = K.um_idx; Q.um_val = K.um_val;
+        Q.T = T->c1_T; Q.col_idx = T->c1_col_idx; Q.row_idx = T->c1_row_idx; Q.coef = T->c1_coef; Q.coef_next = T->c1_coef_next;
+        Q.x_perm = K.xperm; Q.y_perm = K.yperm;
+        CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
+#define C1_LAUNCH(l, nf) dsp_ipm_stage_chain1_kernel<l, 3, nf><<<(unsigned)blocks, 32 * wpb, smem, st>>>(Q)
+        if (NF == 2) { if (L == 4) C1_LAUNCH(4, 2); else if (L == 8) C1_LAUNCH(8, 2); else if (L == 16) C1_LAUNCH(16, 2); else C1_LAUNCH(32, 2); }
+        else { if (L == 4) C1_LAUNCH(4, 3); else if (L == 8) C1_LAUNCH(8, 3); else if (L == 16) C1_LAUNCH(16, 3); else C1_LAUNCH(32, 3); }
+#undef C1_LAUNCH
+        CK(cudaGetLastError());
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_launches++;
+        g_last_grid = (int)blocks; g_last_block = 32 * wpb; g_last_smem = (int)smem; g_last_ppc = per_warp * wpb;
         return 0;
     }
     if (o.kernel == DSP_KERNEL_STAGE || o.kernel == DSP_KERNEL_STAGE_V1) {

@@ -495,3 +495,61 @@ def model_duals(t: LPTemplate, y):
             k = pos[f"row[{mr}]"]
             out[:, r] = y[:, k] * (R[mr] if R is not None else 1.0) * t.meta["sense"]
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def detect_chain1(t: LPTemplate, max_flows=3):
+    """Structure recognition for the descriptor-driven "single storage chain" stage kernel (csrc/dsp_stage_chain1.cuh):
+    every column of the template appears in ONE row (a flow of that period) or in TWO rows that are neighbours in a simple path
+    through all rows (the state carried from one period to the next), at most one state per period and ``max_flows`` flows.
+    Returns None when the template is not of that family, else dict(T, NF, col_idx [T, NF+1], row_idx [T], coef [T, NF+1],
+    coef_next [T]) in template (equilibrated) units -- the kernel needs nothing else that is flowsheet specific."""
+    A = t.A.tocsc()
+    m, n = A.shape
+    cnt = np.diff(A.indptr)
+    if m < 2 or np.any(cnt < 1) or np.any(cnt > 2):
+        return None
+    nbr = [dict() for _ in range(m)]                  # row -> {neighbour row: state column}
+    flows = [[] for _ in range(m)]
+    for j in range(n):
+        rows = A.indices[A.indptr[j]:A.indptr[j + 1]]
+        if len(rows) == 1:
+            flows[rows[0]].append(j)
+        else:
+            a, b = int(rows[0]), int(rows[1])
+            if b in nbr[a]:
+                return None                           # two states between the same pair of periods: K = 2 family
+            nbr[a][b] = j; nbr[b][a] = j
+    deg = np.array([len(d) for d in nbr])
+    if np.any(deg > 2):
+        return None
+    ends = np.flatnonzero(deg <= 1)
+    if len(ends) != 2:
+        return None                                   # a cycle (periodic storage) or several chains
+    order, prev, cur = [], -1, int(ends.min())
+    while True:
+        order.append(cur)
+        nxt = [r for r in nbr[cur] if r != prev]
+        if not nxt:
+            break
+        prev, cur = cur, nxt[0]
+    if len(order) != m:
+        return None
+    T = m
+    # the last period has no successor: its state slot is free and may hold one of its single-row columns
+    NF = max([2] + [len(flows[r]) for r in order[:-1]] + [len(flows[order[-1]]) - 1])
+    if NF > max_flows:
+        return None
+    Acsr = t.A.tocsr()
+    col_idx = -np.ones((T, NF + 1), np.int32); coef = np.zeros((T, NF + 1)); coef_next = np.zeros(T)
+    for k, r in enumerate(order):
+        fl = list(flows[r])
+        if k + 1 < T:
+            j = nbr[r][order[k + 1]]
+            col_idx[k, NF] = j; coef[k, NF] = Acsr[r, j]; coef_next[k] = Acsr[order[k + 1], j]
+        elif len(fl) > NF or fl:
+            j = fl.pop()                              # e.g. the final tank holdup
+            col_idx[k, NF] = j; coef[k, NF] = Acsr[r, j]
+        for f, j in enumerate(fl):
+            col_idx[k, f] = j; coef[k, f] = Acsr[r, j]
+    return dict(T=T, NF=int(NF), col_idx=col_idx, row_idx=np.array(order, np.int32), coef=coef, coef_next=coef_next)

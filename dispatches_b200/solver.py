@@ -27,7 +27,7 @@ STATUS_NAMES = {OPTIMAL: "optimal", MAX_ITER: "maxIterations", NUMERICAL: "error
 
 KERNEL_AUTO, KERNEL_BAND, KERNEL_STAGE, KERNEL_STAGE_V1 = 0, 1, 2, 3
 
-EXPORTS = ["dsp_lp_template_create", "dsp_lp_template_create_csr", "dsp_lp_analyze_csr", "dsp_lp_template_info", "dsp_lp_template_destroy", "dsp_lp_template_set_stage_wb", "dsp_lp_default_opts", "dsp_lp_solve_batch",
+EXPORTS = ["dsp_lp_template_create", "dsp_lp_template_set_stage_chain1", "dsp_lp_template_create_csr", "dsp_lp_analyze_csr", "dsp_lp_template_info", "dsp_lp_template_destroy", "dsp_lp_template_set_stage_wb", "dsp_lp_default_opts", "dsp_lp_solve_batch",
            "dsp_lp_solve_batch_host", "dsp_lp_launch_count", "dsp_lp_last_launch", "dsp_lp_last_error",
            "dsp_lp_version", "dsp_lp_fp64_peak_tflops"]
 
@@ -62,6 +62,11 @@ class _Opts(C.Structure):
                 ("device", C.c_int32), ("reg_primal", C.c_double), ("kernel", C.c_int32)]
 
 
+class _StageChain1(C.Structure):
+    _fields_ = [("T", C.c_int32), ("NF", C.c_int32), ("col_idx", C.c_void_p), ("row_idx", C.c_void_p), ("coef", C.c_void_p),
+                ("coef_next", C.c_void_p)]
+
+
 class _StageWB(C.Structure):
     _fields_ = [("T", C.c_int32), ("a", C.c_double), ("binv", C.c_double), ("half", C.c_double), ("delta", C.c_double),
                 ("dur", C.c_double), ("k_rev", C.c_double), ("wcf_off", C.c_int32), ("p_off", C.c_int32),
@@ -89,6 +94,8 @@ def load_library():
     lib.dsp_lp_template_destroy.restype = None
     lib.dsp_lp_template_set_stage_wb.argtypes = [C.c_void_p, C.POINTER(_StageWB)]
     lib.dsp_lp_template_set_stage_wb.restype = C.c_int
+    lib.dsp_lp_template_set_stage_chain1.argtypes = [C.c_void_p, C.POINTER(_StageChain1)]
+    lib.dsp_lp_template_set_stage_chain1.restype = C.c_int
     lib.dsp_lp_default_opts.argtypes = [C.POINTER(_Opts)]
     lib.dsp_lp_default_opts.restype = None
     lib.dsp_lp_solve_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Opts),
@@ -204,6 +211,17 @@ class BatchLPSolver:
                           col_idx=ci.ctypes.data_as(C.c_void_p), row_idx=ri.ctypes.data_as(C.c_void_p))
             self._check(self.lib.dsp_lp_template_set_stage_wb(self.handle, C.byref(sd)), "dsp_lp_template_set_stage_wb")
             self.has_stage = True
+        # descriptor-driven stage kernel for templates of the single-storage-chain family (structure found on the template itself)
+        self.has_chain1 = False
+        if st is None and kernel != KERNEL_BAND and t.m <= 96:
+            from .lp_template import detect_chain1
+            d1 = detect_chain1(t)
+            if d1 is not None:
+                ci, ri, cf, cn = _i32(d1["col_idx"]), _i32(d1["row_idx"]), _f64(d1["coef"]), _f64(d1["coef_next"])
+                sd = _StageChain1(T=d1["T"], NF=d1["NF"], col_idx=ci.ctypes.data_as(C.c_void_p), row_idx=ri.ctypes.data_as(C.c_void_p),
+                                  coef=cf.ctypes.data_as(C.c_void_p), coef_next=cn.ctypes.data_as(C.c_void_p))
+                self._check(self.lib.dsp_lp_template_set_stage_chain1(self.handle, C.byref(sd)), "dsp_lp_template_set_stage_chain1")
+                self.has_chain1 = True
 
     def close(self):
         if getattr(self, "handle", None):

@@ -92,6 +92,20 @@ typedef struct {
     const int32_t *row_idx;             /* [T*4] template row of (t, r1..r4)                                  */
 } dsp_stage_wb_desc;
 
+/* Stage descriptor of the "single storage chain" family (csrc/dsp_stage_chain1.cuh): ONE row per period; every column appears in
+ * one row (a flow of that period) or in two consecutive rows (the state carried to the next period: tank holdup,
+ * nuclear_flowsheet_multiperiod_class.py:47-49, price_taker_analysis.py:175-178).  Nothing flowsheet specific: indices and row
+ * coefficients of the template itself (dispatches_b200/lp_template.py: detect_chain1 finds them for any template); costs, right-hand
+ * sides and bounds come from the template's parameter maps.  T <= 96, NF = 2 or 3 flow slots per period (absent: col_idx -1).                              */
+typedef struct {
+    int32_t T, NF;
+    const int32_t *col_idx;     /* [T*(NF+1)] template column of (t, flow 0..NF-1 | state), -1 if absent                     */
+    const int32_t *row_idx;     /* [T] template row of period t                                                              */
+    const double  *coef;        /* [T*(NF+1)] coefficient of that column in row t                                            */
+    const double  *coef_next;   /* [T] coefficient of the state of period t in row t+1 (0 for the last period)               */
+} dsp_stage_chain1_desc;
+int dsp_lp_template_set_stage_chain1(dsp_template *t, const dsp_stage_chain1_desc *d);
+
 /* Per-problem status.  DSP_OPTIMAL means: relative primal/dual residuals < feas_tol and relative duality gap < tol; OR, when
  * the complementarity gap has converged (< tol) while residuals / gap sit at the rounding floor of the ill-conditioned normal
  * equations, residuals < 10 feas_tol and gap < 10 tol; OR complementarity < 1e-3 tol with residuals < 100 feas_tol and

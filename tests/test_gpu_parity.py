@@ -477,6 +477,43 @@ def test_native_setup_from_plain_csr(kind):
     assert np.abs(a.x @ t.A.T - b.x @ t.A.T).max() <= 1e-6 * scale          # same feasible point up to the optimal face
 
 
+@pytest.mark.parametrize("T", [48, 24, 7, 96])
+def test_chain1_stage_kernel_against_band_kernel_and_oracle(T):
+    """the descriptor-driven single-storage-chain stage kernel (dsp_stage_chain1.cuh; structure detected on the template) and the
+    generic band kernel run the same algorithm: same objectives / iteration counts on the nuclear dispatch LP (C3), x and y in
+    template order, and the report's tank / turbine LP with batched capacities."""
+    t = TP.nuclear(T)
+    a_sol, b_sol = S.BatchLPSolver(t), S.BatchLPSolver(t, kernel=S.KERNEL_BAND)
+    assert a_sol.has_chain1 and not b_sol.has_chain1
+    p = SC.pool()["cluster_days"]
+    rng = np.random.default_rng(T)
+    N = 1500
+    days = rng.integers(0, len(p) - 4, N)
+    lmp = np.stack([np.concatenate([p[k + i] for i in range(4)])[:T] for k in days]) * rng.lognormal(0, 0.25, (N, T))
+    a = a_sol.solve_host(lmp, None, want_x=True, want_y=True)
+    assert S.last_launch()["block"] % 32 == 0 and S.last_launch()["problems_per_cta"] >= 1
+    b = b_sol.solve_host(lmp, None, want_x=True, want_y=True)
+    assert (a.status == S.OPTIMAL).all() and (b.status == S.OPTIMAL).all()
+    assert rel_err(a.obj, b.obj).max() < 1e-8 and (a.iters == b.iters).mean() > 0.97
+    ref = np.array([H.solve(L.nuclear_raw(l))[0] for l in lmp[:24]]) if T == 48 else None
+    if ref is not None:
+        assert rel_err(a.obj[:24], ref).max() < REL
+    c, bb, u, k = t.instantiate(lmp[0], np.zeros(0))
+    scale = max(1.0, np.abs(u[np.isfinite(u)]).max())
+    assert np.abs(a.x @ t.A.T - bb).max() <= 1e-7 * scale and np.abs(a.y - b.y).max() <= 1e-5 * max(1.0, np.abs(b.y).max())
+    if T == 48:
+        tr = TP.nuclear_report(T, demand=2000.0)
+        sr = S.BatchLPSolver(tr)
+        assert sr.has_chain1
+        lm = SC.pool()["nuc_report_lmp_rt"][1000:1000 + T]
+        cases = [(hp, pem, tank, turb) for hp in (0.75, 1.25, 2.0) for pem in (40.0, 120.0, 200.0) for tank, turb in ((30000.0, 0.0), (50000.0, 40.0), (0.0, 25.0))]
+        cp = np.array([np.r_[lm, c_[0]] for c_ in cases]); rp = np.array([[c_[1], c_[2], c_[3]] for c_ in cases])
+        r = sr.solve_host(cp, rp)
+        refr = np.array([H.solve(L.nuclear_report_raw(lm, hp, pem, pem_capex=400.0, tank_cap=tank, turbine_cap=turb, demand=2000.0))[0]
+                         for hp, pem, tank, turb in cases])
+        assert (r.status == S.OPTIMAL).all() and rel_err(r.obj, refr).max() < REL
+
+
 def test_the_c_abi_from_plain_c(tmp_path):
     """a C program (tests/c_abi_example.c) creates a template from plain CSR, solves a batch, reads x"""
     import subprocess
