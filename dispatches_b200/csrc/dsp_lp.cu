@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -683,6 +684,7 @@ struct dsp_template {
     bool cap_x, cap_y;
     int64_t cap_rp_rows;
     cudaStream_t stream, stream2;
+    std::atomic<int> busy;         // a host call is in flight on this handle (staging buffers, streams and ticket are per handle)
 };
 
 namespace {
@@ -837,7 +839,7 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
     T->has_stage = false; T->has_chain1 = false; T->stage_blocks_per_sm = 0; T->stage2_blocks_per_sm = 0; T->ws = nullptr; T->ws_bytes = 0;
     T->h_cp = T->h_rp = T->h_obj = T->h_x = T->h_y = nullptr; T->h_status = T->h_iters = nullptr;
     T->d_cp = T->d_rp = T->d_obj = T->d_x = T->d_y = nullptr; T->d_status = T->d_iters = nullptr;
-    T->stream = nullptr; T->stream2 = nullptr;
+    T->stream = nullptr; T->stream2 = nullptr; T->busy.store(0);
     CK(cudaGetDevice(&T->device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, T->device));
@@ -1273,9 +1275,27 @@ static int ensure_capacity(dsp_template *T, int64_t N, int64_t rp_rows, bool wan
     return 0;
 }
 
+static int solve_batch_host_locked(dsp_template *T, int64_t N, const double *cparams, const double *rparams,
+                                   int64_t rparams_stride, const dsp_opts *opts, double *obj, int32_t *status,
+                                   int32_t *iters, double *x, double *y);
+
 int dsp_lp_solve_batch_host(dsp_template *T, int64_t N, const double *cparams, const double *rparams,
                             int64_t rparams_stride, const dsp_opts *opts, double *obj, int32_t *status,
                             int32_t *iters, double *x, double *y) {
+    if (!T || N < 0) { g_err = "dsp_lp_solve_batch_host: bad arguments"; return DSP_E_ARG; }
+    int expected = 0;
+    if (!T->busy.compare_exchange_strong(expected, 1)) {       // not re-entrant per handle: enforced, not just documented
+        g_err = "dsp_lp_solve_batch_host: another host call is in flight on this template handle (use one handle per host thread)";
+        return DSP_E_BUSY;
+    }
+    const int rc = solve_batch_host_locked(T, N, cparams, rparams, rparams_stride, opts, obj, status, iters, x, y);
+    T->busy.store(0);
+    return rc;
+}
+
+static int solve_batch_host_locked(dsp_template *T, int64_t N, const double *cparams, const double *rparams,
+                                   int64_t rparams_stride, const dsp_opts *opts, double *obj, int32_t *status,
+                                   int32_t *iters, double *x, double *y) {
     if (!T || N < 0) { g_err = "dsp_lp_solve_batch_host: bad arguments"; return DSP_E_ARG; }
     if (N == 0) return 0;
     const KParams &K = T->kp;

@@ -113,7 +113,7 @@ int dsp_lp_template_set_stage_chain1(dsp_template *t, const dsp_stage_chain1_des
  * the defaults; measured worst case on the 560 640 LPs of config C5: 3e-8).  DSP_INFEASIBLE is reported only for a negative
  * upper bound produced by Umap / rparams (obj = NaN); other infeasible / unbounded LPs end as DSP_MAX_ITER / DSP_NUMERICAL. */
 enum { DSP_OPTIMAL = 0, DSP_MAX_ITER = 1, DSP_NUMERICAL = 2, DSP_INFEASIBLE = 3 };
-enum { DSP_E_ARG = -1, DSP_E_CUDA = -2, DSP_E_SMEM = -3 };
+enum { DSP_E_ARG = -1, DSP_E_CUDA = -2, DSP_E_SMEM = -3, DSP_E_BUSY = -4 /* a host call is already in flight on this handle */ };
 
 /* Replaces: the per-LP model hand-over inside SolverFactory(..).solve(m) (Pyomo LP/NL writer), done once. */
 int dsp_lp_template_create(const dsp_template_desc *desc, dsp_template **out);
@@ -155,7 +155,8 @@ int dsp_lp_solve_batch(const dsp_template *t, int64_t N,
 /* Same with HOST pointers: pinned staging, H2D of the parameters, kernel, D2H of the results, one sync.
  * This is the call the Pyomo plugin / sweep drivers make; bench.py's "e2e" number times it.
  * Page-locked caller buffers are DMA'd directly (no staging copy).  Not re-entrant per template handle: the staging
- * buffers and streams belong to the handle -- use one handle per host thread.                            */
+ * buffers and streams belong to the handle -- use one handle per host thread; a second concurrent call on the same
+ * handle returns DSP_E_BUSY.                                                                            */
 int dsp_lp_solve_batch_host(dsp_template *t, int64_t N,
                             const double *cparams, const double *rparams, int64_t rparams_stride,
                             const dsp_opts *opts,
