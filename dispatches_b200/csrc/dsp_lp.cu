@@ -69,6 +69,12 @@ struct KParams {
     int band_doubles;             // doubles of the (dy, Mb) tail of a work region: what the LDL' / substitution sweeps touch
     int hybrid;                   // workspace mode with the (dy, Mb) tail in shared memory (sweeps at shared-memory latency)
     const int *xperm, *yperm;     // non-null: x_out / y_out index of internal column j / row i (dsp_lp_template_create_csr)
+    // per-problem matrix coefficients (dsp_lp_template_set_matrix_params):  A_val[q] = A0[q] + sum coef * rparams[param]
+    int n_amap;                   // 0: the matrix is shared by the batch
+    const int *amap_q, *amap_param;       // CSR position / rparams index of every term
+    const double *amap_coef;
+    const int *at_from;           // CSC position -> CSR position (A' values follow A's)
+    const int *asm_qa, *asm_qb;   // band assembly: the two CSR positions whose product is asm_val[p]
 };
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -264,12 +270,27 @@ __device__ __forceinline__ void step_pass(const Work &W, const KParams &P, doubl
 }
 
 template <int BW>
-__device__ void solve_one(const Work &W, const Hot &H, const KParams &P, long long p, int lane, double step_frac,
+__device__ void solve_one(const Work &W, const Hot &H0, const KParams &P, long long p, int lane, double step_frac,
                           double reg, int it0, int *status_out, int *iters_out) {
     const int n = P.n, nb = P.nb, m = P.m;
     constexpr int W1 = BW + 1;
     const double *cp = P.cparams + p * (long long)P.Pc;
     const double *rp_ = P.rparams + p * P.rstride;
+    Hot H = H0;
+    if (P.n_amap > 0) {
+        // this LP's own matrix values (free design columns multiplied by per-scenario capacity factors, wind_power.py:120-122):
+        // CSR values, CSC values and the band-assembly products live in the warp's work region behind the band
+        double *Av = W.Mb + (m + BW) * W1, *Atv = Av + P.nnz, *asv = Atv + P.nnz;
+        for (int q = lane; q < P.nnz; q += 32) Av[q] = H0.A_val[q];
+        __syncwarp();
+        if (lane == 0)
+            for (int k = 0; k < P.n_amap; ++k) Av[P.amap_q[k]] += P.amap_coef[k] * rp_[P.amap_param[k]];
+        __syncwarp();
+        for (int q = lane; q < P.nnz; q += 32) Atv[q] = Av[P.at_from[q]];
+        for (int q = lane; q < P.nasm; q += 32) asv[q] = Av[P.asm_qa[q]] * Av[P.asm_qb[q]];
+        __syncwarp();
+        H.A_val = Av; H.At_val = Atv; H.asm_val = asv;
+    }
     // ---- instantiate c, b, u, objective constant from the parameter maps
     double cmax = 0.0, bmax = 0.0, kconst = 0.0;
     for (int j = lane; j < n; j += 32) {
@@ -674,6 +695,7 @@ struct dsp_template {
     int smem_optin;
     std::vector<void *> dev_allocs;
     std::vector<int> col_perm, row_perm;     // dsp_lp_template_create_csr: caller index of internal column / row
+    std::vector<int> csr_ptr, csr_idx, asm_qa, asm_qb;   // permuted CSR pattern + assembly factor positions (kept for matrix parameters)
     unsigned long long *ticket;
     // host-call staging (pinned) and device buffers, grown on demand
     int64_t cap_N;
@@ -1392,6 +1414,7 @@ struct CsrAnalysis {
     std::vector<double> A_val;
     std::vector<int> asm_ptr, asm_col;
     std::vector<double> asm_val;
+    std::vector<int> asm_qa, asm_qb;          // CSR positions of the two factors of every assembly term
 };
 
 int bandwidth_of(const std::vector<std::vector<int>> &adj, const std::vector<int> &pos) {
@@ -1480,21 +1503,23 @@ int analyze_csr(const dsp_lp_desc *D, CsrAnalysis &R) {
         std::sort(ent.begin(), ent.end());
         for (size_t e = 0; e < ent.size(); ++e) { R.A_idx[R.A_ptr[k] + e] = ent[e].first; R.A_val[R.A_ptr[k] + e] = ent[e].second; }
     }
-    // 4. assembly list of the lower band of M = A D A':  M[i][i-k] = sum coef * d[col]
+    // 4. assembly list of the lower band of M = A D A':  M[i][i-k] = sum coef * d[col]   (coef = A[i][col] * A[i-k][col])
     const int w = R.w;
-    std::vector<std::vector<std::pair<int, double>>> ent((size_t)m * (w + 1));
-    std::vector<std::vector<std::pair<int, double>>> col_rows(n);       // (new row, value) per new column
+    struct Term { int col, qa, qb; double v; };
+    std::vector<std::vector<Term>> ent((size_t)m * (w + 1));
+    struct RowEnt { int row, q; double v; };
+    std::vector<std::vector<RowEnt>> col_rows(n);       // (new row, CSR position, value) per new column
     for (int k = 0; k < m; ++k)
-        for (int q = R.A_ptr[k]; q < R.A_ptr[k + 1]; ++q) col_rows[R.A_idx[q]].emplace_back(k, R.A_val[q]);
+        for (int q = R.A_ptr[k]; q < R.A_ptr[k + 1]; ++q) col_rows[R.A_idx[q]].push_back({k, q, R.A_val[q]});
     for (int j = 0; j < n; ++j)
         for (auto &ra : col_rows[j])
             for (auto &rb : col_rows[j])
-                if (rb.first <= ra.first) ent[(size_t)ra.first * (w + 1) + (ra.first - rb.first)].emplace_back(j, ra.second * rb.second);
+                if (rb.row <= ra.row) ent[(size_t)ra.row * (w + 1) + (ra.row - rb.row)].push_back({j, ra.q, rb.q, ra.v * rb.v});
     R.asm_ptr.assign((size_t)m * (w + 1) + 1, 0);
-    R.asm_col.clear(); R.asm_val.clear();
+    R.asm_col.clear(); R.asm_val.clear(); R.asm_qa.clear(); R.asm_qb.clear();
     for (size_t e = 0; e < ent.size(); ++e) {
         R.asm_ptr[e + 1] = R.asm_ptr[e] + (int)ent[e].size();
-        for (auto &cv : ent[e]) { R.asm_col.push_back(cv.first); R.asm_val.push_back(cv.second); }
+        for (auto &t : ent[e]) { R.asm_col.push_back(t.col); R.asm_val.push_back(t.v); R.asm_qa.push_back(t.qa); R.asm_qb.push_back(t.qb); }
     }
     return 0;
 }
@@ -1554,6 +1579,7 @@ int dsp_lp_template_create_csr(const dsp_lp_desc *D, dsp_template **out) {
     rc = dsp_lp_template_create(&d, &T);
     if (rc) return rc;
     T->col_perm = R.col_perm; T->row_perm = R.row_perm;
+    T->csr_ptr = R.A_ptr; T->csr_idx = R.A_idx; T->asm_qa = R.asm_qa; T->asm_qb = R.asm_qb;
     int *dx = nullptr, *dy = nullptr;
     rc = upload(R.col_perm, &dx);
     if (!rc) { T->dev_allocs.push_back(dx); rc = upload(R.row_perm, &dy); }
@@ -1561,6 +1587,48 @@ int dsp_lp_template_create_csr(const dsp_lp_desc *D, dsp_template **out) {
     T->dev_allocs.push_back(dy);
     T->kp.xperm = dx; T->kp.yperm = dy;
     *out = T;
+    return 0;
+}
+
+int dsp_lp_template_set_matrix_params(dsp_template *T, int32_t count, const int32_t *row, const int32_t *col, const int32_t *param,
+                                      const double *coef) {
+    if (!T || count < 0 || (count > 0 && (!row || !col || !param || !coef))) { g_err = "dsp_lp_template_set_matrix_params: bad arguments"; return DSP_E_ARG; }
+    if (T->csr_ptr.empty()) { g_err = "dsp_lp_template_set_matrix_params: the template must come from dsp_lp_template_create_csr"; return DSP_E_ARG; }
+    if (T->kp.w != 1 && T->kp.w != 2 && T->kp.w != 4 && T->kp.w != 8 && T->kp.w != 16 && T->kp.w != 32) { g_err = "bad band"; return DSP_E_ARG; }
+    KParams &K = T->kp;
+    const int m = K.m, n = K.n, nnz = K.nnz;
+    std::vector<int> cpos(n), rpos(m);
+    for (int k = 0; k < n; ++k) cpos[T->col_perm[k]] = k;
+    for (int k = 0; k < m; ++k) rpos[T->row_perm[k]] = k;
+    std::vector<int> q(count), pr(count);
+    std::vector<double> cf(count);
+    for (int k = 0; k < count; ++k) {
+        if (row[k] < 0 || row[k] >= m || col[k] < 0 || col[k] >= n || param[k] < 0 || param[k] >= K.Pr) { g_err = "matrix parameter index out of range"; return DSP_E_ARG; }
+        const int i = rpos[row[k]], j = cpos[col[k]];
+        int pos = -1;
+        for (int t = T->csr_ptr[i]; t < T->csr_ptr[i + 1]; ++t) if (T->csr_idx[t] == j) pos = t;
+        if (pos < 0) { g_err = "matrix parameter on an entry that is not in the sparsity pattern of A (store an explicit nominal value)"; return DSP_E_ARG; }
+        q[k] = pos; pr[k] = param[k]; cf[k] = coef[k];
+    }
+    // CSC position -> CSR position: the same stable counting sort dsp_lp_template_create used for the values
+    std::vector<int> At_ptr(n + 1, 0), at_from(nnz);
+    for (int t = 0; t < nnz; ++t) At_ptr[T->csr_idx[t] + 1]++;
+    for (int j = 0; j < n; ++j) At_ptr[j + 1] += At_ptr[j];
+    {
+        std::vector<int> fill(At_ptr.begin(), At_ptr.end() - 1);
+        for (int i = 0; i < m; ++i)
+            for (int t = T->csr_ptr[i]; t < T->csr_ptr[i + 1]; ++t) at_from[fill[T->csr_idx[t]]++] = t;
+    }
+    int *dq, *dp, *daf, *dqa, *dqb; double *dc;
+    int rc = upload(q, &dq); if (rc) return rc; T->dev_allocs.push_back(dq);
+    rc = upload(pr, &dp); if (rc) return rc; T->dev_allocs.push_back(dp);
+    rc = upload(cf, &dc); if (rc) return rc; T->dev_allocs.push_back(dc);
+    rc = upload(at_from, &daf); if (rc) return rc; T->dev_allocs.push_back(daf);
+    rc = upload(T->asm_qa, &dqa); if (rc) return rc; T->dev_allocs.push_back(dqa);
+    rc = upload(T->asm_qb, &dqb); if (rc) return rc; T->dev_allocs.push_back(dqb);
+    if (K.n_amap == 0) { K.prob_doubles += 2 * nnz + K.nasm; K.band_doubles += 2 * nnz + K.nasm; }   // this LP's matrix values sit behind its band (in every placement)
+    K.n_amap = count; K.amap_q = dq; K.amap_param = dp; K.amap_coef = dc; K.at_from = daf; K.asm_qa = dqa; K.asm_qb = dqb;
+    if (count == 0) K.n_amap = 0;
     return 0;
 }
 

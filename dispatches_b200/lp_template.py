@@ -54,6 +54,8 @@ class LPTemplate:
     asm_ptr: np.ndarray | None = None
     asm_col: np.ndarray | None = None
     asm_val: np.ndarray | None = None
+    # per-problem matrix coefficients: A[row, col] = A0[row, col] + sum coef * rparams[param]  (rows / cols in template order)
+    amap: tuple | None = None        # (rows, cols, params, coefs) int / int / int / float arrays
 
     @property
     def m(self):
@@ -87,6 +89,17 @@ class LPTemplate:
         u[fin] = u[fin] + (self.Umap @ rparams)[fin]
         return c, b, u, self.o0 + float(self.omap @ rparams) + float(self.ocmap @ cparams)
 
+    def matrix(self, rparams):
+        """the constraint matrix of one problem (A itself when the template has no matrix parameters)"""
+        if self.amap is None:
+            return self.A
+        r, c, k, v = self.amap
+        A = self.A.tolil(copy=True)
+        rparams = np.asarray(rparams, float)
+        for i, j, kk, vv in zip(r, c, k, v):
+            A[i, j] = A[i, j] + vv * rparams[kk]
+        return A.tocsr()
+
     # ------------------------------------------------------------------
     def finalize(self, equilibrate=False):
         """Column order (bounded first), row order (min bandwidth of A A'), band assembly list."""
@@ -100,6 +113,9 @@ class LPTemplate:
         self.u0 = self.u0[cperm]; self.Umap = self.Umap.tocsr()[cperm]
         self.col_shift = self.col_shift[cperm]; self.col_scale = self.col_scale[cperm]
         self.col_names = [self.col_names[j] for j in cperm]
+        if self.amap is not None:
+            inv = np.empty(n, int); inv[cperm] = np.arange(n)
+            self.amap = (self.amap[0], inv[self.amap[1]], self.amap[2], self.amap[3])
         # 1b. geometric-mean equilibration  A <- R A C  (x = C x~, b~ = R b, c~ = C c, u~ = u / C)
         if equilibrate:
             A = A.tocsr().astype(float)
@@ -120,6 +136,8 @@ class LPTemplate:
             self.u0 = self.u0 / C; self.Umap = (sp.diags(1.0 / C) @ self.Umap).tocsr()
             self.col_scale = self.col_scale * C
             self.meta["row_scale"] = R
+            if self.amap is not None:
+                self.amap = (self.amap[0], self.amap[1], self.amap[2], self.amap[3] * R[self.amap[0]] * C[self.amap[1]])
         # 2. row order: natural vs reverse Cuthill-McKee on the pattern of A A'
         P = (abs(A) @ abs(A).T).tocsr()
         P.data[:] = 1.0
@@ -137,6 +155,9 @@ class LPTemplate:
         A = A[perm]
         self.b0 = self.b0[perm]; self.Bmap = self.Bmap.tocsr()[perm]
         self.row_names = [self.row_names[i] for i in perm]
+        if self.amap is not None:
+            invr = np.empty(m, int); invr[perm] = np.arange(m)
+            self.amap = (invr[self.amap[0]], self.amap[1], self.amap[2], self.amap[3])
         self.A = A.tocsr(); self.A.sort_indices()
         # 3. assembly list of the lower band of M = A D A'
         w = self.w
@@ -191,6 +212,7 @@ class TemplateBuilder:
         self.c = []                            # (const, {k: coef})
         self.arows, self.rhs = [], []          # dict col->val ; (const, {k:coef})
         self.o0, self.omap = 0.0, np.zeros(Pr)
+        self.acoef = []                        # (row, col, rparam, coef): per-problem matrix coefficients
         self.meta = {}
 
     @staticmethod
@@ -216,7 +238,17 @@ class TemplateBuilder:
         self.c[j] = (c0 + a0, cm)
 
     def eq(self, name, coeffs, rhs=0.0):
-        self.rows.append(name); self.arows.append(dict(coeffs)); self.rhs.append(self._aff(rhs))
+        """coefficients are floats, or ``(nominal, {k: coef})`` for an entry that varies per problem with rparams[k] (the nominal value
+        keeps the entry in the sparsity pattern and is what the once-per-template scaling sees)"""
+        plain = {}
+        for j, v in dict(coeffs).items():
+            if isinstance(v, tuple):
+                plain[j] = float(v[0])
+                for k, cf in v[1].items():
+                    self.acoef.append((len(self.rows), j, int(k), float(cf)))
+            else:
+                plain[j] = v
+        self.rows.append(name); self.arows.append(plain); self.rhs.append(self._aff(rhs))
 
     def le(self, name, coeffs, rhs=0.0):
         s = self.var("slack:" + name)
@@ -273,6 +305,12 @@ class TemplateBuilder:
         u0, Umap = affine_rows(self.u, self.Pr, default=INF)
         t = LPTemplate(self.name, A, b0, Bmap, c0, Cmap, u0, Umap, self.o0, self.omap.copy(), self.ocmap.copy(),
                        shifts.copy(), np.ones(n), list(self.cols), list(self.rows), dict(self.meta))
+        if self.acoef:
+            for r, j, k, cf in self.acoef:
+                if lbs[j] != 0.0 or j not in remap:
+                    raise ValueError("a per-problem matrix coefficient needs a free-standing column with lower bound 0")
+            t.amap = (np.array([a[0] for a in self.acoef], int), np.array([remap[a[1]] for a in self.acoef], int),
+                      np.array([a[2] for a in self.acoef], int), np.array([a[3] for a in self.acoef], float))
         return t.finalize(equilibrate=equilibrate)
 
 

@@ -142,19 +142,28 @@ def wind_battery_optimize(n_time_points, input_params, verbose=False, want_solut
 
 def _wind_battery_free_wind(T, lmp, cf, input_params, verbose):
     """design_opt=True, extant_wind=False: battery and wind size are decisions (wind_battery_LMP.py:209-219).  cf_t
-    multiplies the wind-capacity column, so the capacity-factor series is part of the template: one series per call,
-    batched over the LMP scenarios."""
+    multiplies the wind-capacity column: with ONE series it is baked into the template (batch over LMP scenarios); with a
+    series per scenario the cf_t become per-problem matrix coefficients of the band kernel."""
     cf = np.asarray(cf, float)
-    if cf.ndim != 1:
-        if not np.all(cf == cf[:1]):
-            raise NotImplementedError("design_opt with a free wind size: one capacity-factor series per call "
-                                      "(cf_t enters the constraint matrix, which the batch shares)")
-        cf = cf[0]
-    key = ("wind_battery_design_free_wind", T, cf.tobytes(), float(input_params.get("wind_mw_ub", 10000.0)))
-    if key not in _SOLVERS:
-        _SOLVERS[key] = BatchLPSolver(TP.wind_battery_design_free_wind(T, cf, key[3]))
+    ub = float(input_params.get("wind_mw_ub", 10000.0))
+    rp = None
+    if cf.ndim != 1 and not np.all(cf == cf[:1]):
+        # a capacity-factor series per batch member: cf_t multiplies the wind-capacity column, i.e. it is a coefficient of the
+        # constraint matrix -> per-problem matrix coefficients (templates.wind_battery_design_free_wind(cf=None))
+        if cf.shape[0] != lmp.shape[0]:
+            raise ValueError("wind_resource must be one series or one per LMP scenario")
+        key = ("wind_battery_design_free_wind_cfbatched", T, ub)
+        if key not in _SOLVERS:
+            _SOLVERS[key] = BatchLPSolver(TP.wind_battery_design_free_wind(T, None, ub))
+        rp = np.ascontiguousarray(cf - TP.CF_NOMINAL)
+    else:
+        if cf.ndim != 1:
+            cf = cf[0]
+        key = ("wind_battery_design_free_wind", T, cf.tobytes(), ub)
+        if key not in _SOLVERS:
+            _SOLVERS[key] = BatchLPSolver(TP.wind_battery_design_free_wind(T, cf, ub))
     sol = _SOLVERS[key]
-    r = sol.solve_host(lmp, None, want_x=True)
+    r = sol.solve_host(lmp, rp, want_x=True)
     if verbose:
         print(f"b200ipm: {lmp.shape[0]} LPs, iterations mean {r.iters.mean():.1f} max {r.iters.max()}, "
               f"non-optimal {(r.status != OPTIMAL).sum()}")

@@ -27,7 +27,7 @@ STATUS_NAMES = {OPTIMAL: "optimal", MAX_ITER: "maxIterations", NUMERICAL: "error
 
 KERNEL_AUTO, KERNEL_BAND, KERNEL_STAGE, KERNEL_STAGE_V1 = 0, 1, 2, 3
 
-EXPORTS = ["dsp_lp_template_create", "dsp_lp_template_set_stage_chain1", "dsp_lp_template_create_csr", "dsp_lp_analyze_csr", "dsp_lp_template_info", "dsp_lp_template_destroy", "dsp_lp_template_set_stage_wb", "dsp_lp_default_opts", "dsp_lp_solve_batch",
+EXPORTS = ["dsp_lp_template_create", "dsp_lp_template_set_matrix_params", "dsp_lp_template_set_stage_chain1", "dsp_lp_template_create_csr", "dsp_lp_analyze_csr", "dsp_lp_template_info", "dsp_lp_template_destroy", "dsp_lp_template_set_stage_wb", "dsp_lp_default_opts", "dsp_lp_solve_batch",
            "dsp_lp_solve_batch_host", "dsp_lp_launch_count", "dsp_lp_last_launch", "dsp_lp_last_error",
            "dsp_lp_version", "dsp_lp_fp64_peak_tflops"]
 
@@ -88,6 +88,8 @@ def load_library():
     lib.dsp_lp_template_create_csr.restype = C.c_int
     lib.dsp_lp_analyze_csr.argtypes = [C.POINTER(_LpDesc)] + [C.POINTER(C.c_int32)] * 4 + [C.c_void_p, C.c_void_p]
     lib.dsp_lp_analyze_csr.restype = C.c_int
+    lib.dsp_lp_template_set_matrix_params.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dsp_lp_template_set_matrix_params.restype = C.c_int
     lib.dsp_lp_template_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
     lib.dsp_lp_template_info.restype = C.c_int
     lib.dsp_lp_template_destroy.argtypes = [C.c_void_p]
@@ -156,6 +158,8 @@ class BatchLPSolver:
         self.t = template
         t = template
         nb = t.nb
+        if t.amap is not None:
+            native_setup = True          # per-problem matrix coefficients need the library's own symbolic setup
         A = t.A.tocsr(); A.sort_indices()
         Cm = t.Cmap.tocsr(); Bm = t.Bmap.tocsr()
         h = C.c_void_p()
@@ -197,6 +201,12 @@ class BatchLPSolver:
             if rc != 0:
                 raise RuntimeError(f"dsp_lp_template_create failed ({rc}): {self.lib.dsp_lp_last_error().decode()}")
         self.handle = h
+        if t.amap is not None:
+            ar, ac, ak, av = _i32(t.amap[0]), _i32(t.amap[1]), _i32(t.amap[2]), _f64(t.amap[3])
+            vp_ = lambda a: a.ctypes.data_as(C.c_void_p)
+            rc = self.lib.dsp_lp_template_set_matrix_params(h, len(ar), vp_(ar), vp_(ac), vp_(ak), vp_(av))
+            if rc != 0:
+                raise RuntimeError(f"dsp_lp_template_set_matrix_params failed ({rc}): {self.lib.dsp_lp_last_error().decode()}")
         self.opts = _Opts()
         self.lib.dsp_lp_default_opts(C.byref(self.opts))
         self.opts.tol, self.opts.feas_tol, self.opts.max_iter, self.opts.step_frac = tol, feas_tol, max_iter, step_frac

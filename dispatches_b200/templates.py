@@ -134,17 +134,26 @@ def wind_battery_design(T: int, extant_wind: bool = True) -> LPTemplate:
     return B.build()
 
 
-def wind_battery_design_free_wind(T: int, cf, wind_mw_ub: float = 10000.0) -> LPTemplate:
+CF_NOMINAL = 0.35      # nominal capacity factor of the per-problem wind rows (keeps the entry in the pattern; scaling sees it)
+
+
+def wind_battery_design_free_wind(T: int, cf=None, wind_mw_ub: float = 10000.0) -> LPTemplate:
     """wind_battery_optimize with design_opt=True and extant_wind=False (wind_battery_LMP.py:209-219, :256-263): battery
     AND wind size are decisions.  The wind row  electricity <= system_capacity * cf_t  (wind_power.py:120-122) puts cf_t
     into the constraint matrix, which the batch shares -- so this template is built for ONE capacity-factor series
     (the reference's design runs use the site's series with many price signals) and batched over LMPs only.
     wind_system_capacity >= system_capacity[t] (:218) is tight at the optimum (no other cost on system_capacity[t]); as
     for the battery, one capacity column per period + link equalities keeps the matrix banded.
-    cparams = lmp[T];  rparams = [] ."""
-    cf = np.asarray(cf, float)
-    assert cf.shape == (T,)
-    B = TemplateBuilder(f"wind_battery_design_free_wind_T{T}", Pc=T, Pr=0)
+    cparams = lmp[T];  rparams = [] .
+
+    ``cf=None`` (round 2): the capacity factors become PER-PROBLEM matrix coefficients -- rparams = cf_t - CF_NOMINAL (T values),
+    entry -(CF_NOMINAL + rparams[t]) on system_capacity[t] -- so a batch may carry a different wind series per member
+    (dsp_lp_template_set_matrix_params; the band kernel re-derives A, A' and the band products per LP)."""
+    per_problem = cf is None
+    if not per_problem:
+        cf = np.asarray(cf, float)
+        assert cf.shape == (T,)
+    B = TemplateBuilder(f"wind_battery_design_free_wind_T{T}" + ("_cfbatched" if per_problem else ""), Pc=T, Pr=T if per_problem else 0)
     ann = 52.0 / (T / 168.0)
     k_rev = -1e-5 * PA * ann * 1e-3
     cap = BATT_CAP_COST_KW + BATT_CAP_COST_KWH * DURATION
@@ -173,11 +182,11 @@ def wind_battery_design_free_wind(T: int, cf, wind_mw_ub: float = 10000.0) -> LP
         B.le(f"power_bound_in[{t}]", {i[t]: 1.0, Pn[t]: -1.0})
         B.le(f"power_bound_out[{t}]", {o[t]: 1.0, Pn[t]: -1.0})
         B.le(f"soc_bound[{t}]", {s[t]: 1.0, e[t]: DEGRADATION, Pn[t]: -DURATION})
-        B.le(f"wind[{t}]", {g[t]: 1.0, i[t]: 1.0, Wn[t]: -float(cf[t])})
+        B.le(f"wind[{t}]", {g[t]: 1.0, i[t]: 1.0, Wn[t]: ((-CF_NOMINAL, {t: -1.0}) if per_problem else -float(cf[t]))})
         if t < T - 1:
             B.eq(f"link_nameplate[{t}]", {Pn[t]: 1.0, Pn[t + 1]: -1.0})
             B.eq(f"link_wind[{t}]", {Wn[t]: 1.0, Wn[t + 1]: -1.0})
-    B.meta.update(kind="wind_battery_design_free_wind", T=T, ann=ann)
+    B.meta.update(kind="wind_battery_design_free_wind", T=T, ann=ann, per_problem_cf=per_problem)
     return B.build(equilibrate=True)
 
 

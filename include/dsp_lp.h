@@ -137,6 +137,12 @@ int dsp_lp_template_create_csr(const dsp_lp_desc *desc, dsp_template **out);
 int dsp_lp_analyze_csr(const dsp_lp_desc *desc, int32_t *nb, int32_t *w, int32_t *w_natural, int32_t *w_rcm,
                        int32_t *col_perm /*[n] or NULL*/, int32_t *row_perm /*[m] or NULL*/);
 int dsp_lp_template_info(const dsp_template *t, int32_t *m, int32_t *n, int32_t *nb, int32_t *w);
+/* Per-problem MATRIX coefficients for a template made by dsp_lp_template_create_csr:  A[row][col] = A0[row][col] + sum coef * rparams[param]
+ * (row / col in the caller's order; the entry must be in A's pattern).  Needed where a design column is multiplied by per-scenario data --
+ * wind system_capacity * capacity_factor[t] with a free wind size, wind_power.py:120-122 + wind_battery_LMP.py:212-216.  The band kernel then
+ * re-derives A, A' and the band-assembly products per LP inside its work region (2 nnz + nasm more doubles per LP in flight).        */
+int dsp_lp_template_set_matrix_params(dsp_template *t, int32_t count, const int32_t *row, const int32_t *col, const int32_t *param,
+                                      const double *coef);
 
 /* Optional: registers the stage structure of a wind+battery template (see dsp_stage_wb_desc). */
 int dsp_lp_template_set_stage_wb(dsp_template *t, const dsp_stage_wb_desc *d);

@@ -351,6 +351,27 @@ def test_design_opt_free_wind():
         assert res.sizes["wind_kw"][k] == pytest.approx(xr[raw.meta["Wc"]], rel=1e-4, abs=50.0)
 
 
+def test_design_opt_free_wind_with_per_scenario_capacity_factors():
+    """per-problem MATRIX coefficients (dsp_lp_template_set_matrix_params): design_opt=True, extant_wind=False with a different
+    wind series per LMP scenario through the reference-shaped API; objective and optimal sizes against the raw oracle LP."""
+    lmp, cf, W, P = SC.c2(48)
+    rng = np.random.default_rng(4)
+    cfs = np.clip(cf[None, :] * rng.uniform(0.4, 1.6, (48, 24)), 0.0, 1.0)
+    scale = np.where(np.arange(48) % 2 == 1, 20.0, 1.0)[:, None]
+    ip = {"wind_mw": W, "wind_mw_ub": 10000, "batt_mw": P, "design_opt": True, "extant_wind": False,
+          "wind_resource": cfs, "DA_LMPs": lmp * scale}
+    res = PT.wind_battery_optimize(24, ip)
+    assert np.all(res.status == S.OPTIMAL)
+    built = 0
+    for k in range(0, 48, 3):
+        raw = L.wind_battery_raw(lmp[k] * scale[k, 0], cfs[k], W, P, design_opt=True, extant_wind=False)
+        ref, xr = H.solve(raw)
+        assert rel_err(res.obj[k], ref) < REL
+        assert res.sizes["wind_kw"][k] == pytest.approx(xr[raw.meta["Wc"]], rel=1e-3, abs=100.0)
+        built += xr[raw.meta["Wc"]] > 1e3
+    assert built >= 3                                  # some scenarios do build wind
+
+
 def test_design_opt_pem_mode():
     """design_opt="PEM" (run_pricetaker_wind_PEM.py:36-37, pem_ratio None): PEM size optimised, battery fixed at 0."""
     lmp, cf, W, P = SC.c2(40)

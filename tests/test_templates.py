@@ -169,3 +169,24 @@ def test_nuclear_report_with_tank_and_turbine_matches_raw_oracle(tank, turb, dem
         obj, x = solve_template(t, np.r_[lmp, hp], np.array([pem, tank, turb]))
         ref, xr = H.solve(L.nuclear_report_raw(lmp, hp, pem, pem_capex=400.0, tank_cap=tank, turbine_cap=turb, demand=demand))
         assert obj == pytest.approx(ref, rel=1e-10)
+
+
+def test_free_wind_with_a_capacity_factor_series_per_problem_matches_raw_oracle():
+    """design_opt=True, extant_wind=False with a DIFFERENT capacity-factor series per batch member: cf_t multiplies the wind-capacity
+    column (wind_power.py:120-122), i.e. it is a matrix coefficient -- LPTemplate.amap / matrix()"""
+    from scipy.optimize import linprog
+    T = 24
+    t = TP.wind_battery_design_free_wind(T)
+    assert t.amap is not None and len(t.amap[0]) == T and t.Pr == T
+    lmp, cf, W, P = SC.c2(3)
+    rng = np.random.default_rng(0)
+    for k in range(3):
+        cfk = np.clip(cf * rng.uniform(0.5, 1.5, T), 0, 1)
+        c, b, u, kc = t.instantiate(lmp[k] * 20, cfk - TP.CF_NOMINAL)
+        for opts in (dict(primal_feasibility_tolerance=1e-10, dual_feasibility_tolerance=1e-10), dict()):
+            r = linprog(c, A_eq=t.matrix(cfk - TP.CF_NOMINAL), b_eq=b, bounds=[(0, None if not np.isfinite(v) else v) for v in u],
+                        method="highs-ds", options=opts)
+            if r.status == 0:
+                break
+        ref, _ = H.solve(L.wind_battery_raw(lmp[k] * 20, cfk, W, P, design_opt=True, extant_wind=False))
+        assert r.fun + kc == pytest.approx(ref, rel=1e-10)
