@@ -241,9 +241,11 @@ def test_reference_shaped_api():
     assert res.annual_revenue[0] == pytest.approx(rep["annual_revenue"], rel=1e-5)
     soc, wind_gen, b2g, w2g, w2b, rev, lmps, wcap, bcap, ann, npv = PT.record_results(res, 0)
     assert len(soc) == 24 and soc[-1] == 0.0 and wcap == pytest.approx(W) and npv == pytest.approx(res.NPV[0])
-    with pytest.raises(NotImplementedError):     # a free wind size needs one capacity-factor series for the whole batch
-        PT.wind_battery_optimize(24, dict(params, design_opt=True, extant_wind=False,
-                                          wind_resource=np.stack([cf * (1 - 0.01 * k) for k in range(16)])))
+    # a free wind size with one capacity-factor series per scenario: per-problem matrix coefficients (round 2; refused in round 1)
+    cfs = np.stack([cf * (1 - 0.01 * k) for k in range(16)])
+    r2 = PT.wind_battery_optimize(24, dict(params, design_opt=True, extant_wind=False, wind_resource=cfs))
+    assert (r2.status == S.OPTIMAL).all()
+    assert rel_err(r2.obj[5], H.solve(L.wind_battery_raw(lmp[5], cfs[5], W, P, design_opt=True, extant_wind=False))[0]) < REL
 
 
 def test_sweep_drivers_write_reference_shaped_results(tmp_path):

@@ -17,10 +17,11 @@ def reference_params(lmp, cf, W, P, **kw):
 
 def test_design_opt_is_refused_not_silently_fixed():
     lmp, cf, W, P = SC.c2(2)
-    # a free wind size needs ONE capacity-factor series per call (cf_t enters the shared constraint matrix)
+    # a free wind size with one capacity-factor series per scenario is a per-problem MATRIX coefficient (supported since round 2);
+    # what is still refused is a series count that matches neither 1 nor the number of scenarios
     params = reference_params(lmp, cf, W, P, design_opt=True, extant_wind=False)
-    params["wind_resource"] = np.stack([cf, 0.5 * cf])
-    with pytest.raises(NotImplementedError):
+    params["wind_resource"] = np.stack([cf, 0.5 * cf, 0.25 * cf])
+    with pytest.raises(ValueError):
         PT.wind_battery_optimize(24, params)
     with pytest.raises(NotImplementedError):
         PT.wind_battery_pem_optimize(24, reference_params(lmp, cf, W, P, design_opt=True, pem_mw=100, h2_price_per_kg=2))

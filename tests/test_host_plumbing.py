@@ -22,7 +22,7 @@ class HighsStandIn:
             r_ = np.zeros(0) if rp is None else (rp if np.ndim(rp) == 1 else rp[k])
             c, b, u, kk = self.t.instantiate(cp[k], r_)
             for opts in (dict(primal_feasibility_tolerance=1e-10, dual_feasibility_tolerance=1e-10), {}):
-                r = linprog(c, A_eq=self.t.A, b_eq=b, bounds=[(0, None if not np.isfinite(v) else v) for v in u],
+                r = linprog(c, A_eq=self.t.matrix(r_), b_eq=b, bounds=[(0, None if not np.isfinite(v) else v) for v in u],
                             method="highs-ds", options=opts)
                 if r.status == 0:
                     break
