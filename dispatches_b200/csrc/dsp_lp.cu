@@ -609,6 +609,7 @@ __global__ void __launch_bounds__(32 * kStage2Warps, 1) dsp_ipm_stage2_wb_kernel
 }  // namespace
 
 #include "dsp_stage_chain1.cuh"
+#include "dsp_stage2_long.cuh"
 
 namespace {
 // descriptor-driven stage kernel of the single-storage-chain family (dsp_stage_chain1.cuh): same CTA shape as stage2
@@ -619,6 +620,12 @@ __global__ void __launch_bounds__(32 * kChain1Warps, 1) dsp_ipm_stage_chain1_ker
 }
 inline int chain1_lanes(int T) { return T <= 12 ? 4 : T <= 24 ? 8 : T <= 48 ? 16 : 32; }
 constexpr int kChain1MaxT = 96;
+
+// long horizons (T > 96) of the wind+battery structure: one warp per LP, state in a global workspace (dsp_stage2_long.cuh)
+constexpr int kLongWarps = 4;
+__global__ void __launch_bounds__(32 * kLongWarps) dsp_ipm_stage2_long_kernel(const stage2long::LongParams LQ) {
+    stage2long::warp_body_long(LQ, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), threadIdx.x & 31);
+}
 
 struct Stage2Geom { int L, P; };
 inline Stage2Geom stage2_geometry(int T) {
@@ -943,7 +950,7 @@ int dsp_lp_template_create(const dsp_template_desc *D, dsp_template **out) {
 }
 
 int dsp_lp_template_set_stage_wb(dsp_template *T, const dsp_stage_wb_desc *d) {
-    if (!T || !d || d->T < 1 || d->T > kStage2MaxT) { g_err = "dsp_lp_template_set_stage_wb: need 1 <= T <= 96"; return DSP_E_ARG; }
+    if (!T || !d || d->T < 1) { g_err = "dsp_lp_template_set_stage_wb: need T >= 1"; return DSP_E_ARG; }
     if (T->kp.Pc < d->T || T->kp.Pr <= std::max(d->wcf_off + d->T - 1, d->p_off)) {
         g_err = "dsp_lp_template_set_stage_wb: parameter layout does not fit the template";
         return DSP_E_ARG;
@@ -962,7 +969,7 @@ int dsp_lp_template_set_stage_wb(dsp_template *T, const dsp_stage_wb_desc *d) {
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dsp_ipm_stage_wb_kernel, 32 * DSP_STAGE_WPB, 0));
     T->stage_blocks_per_sm = std::max(nb, 1);
-    {
+    if (d->T <= kStage2MaxT) {
         const Stage2Geom g = stage2_geometry(d->T);
         const size_t smem = stage2_smem_bytes(g) * kStage2Warps;
         for (int sync = 0; sync < 2; ++sync) {
@@ -1093,6 +1100,43 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
     K.tol = o.tol; K.feas_tol = o.feas_tol; K.step_frac = o.step_frac; K.reg = o.reg_primal; K.max_iter = o.max_iter;
     K.obj = obj; K.status = status; K.iters = iters; K.x_out = x; K.y_out = y;
     K.ticket = ticket;
+    if (T->has_stage && T->sp.T > kStage2MaxT && (o.kernel == DSP_KERNEL_AUTO || o.kernel == DSP_KERNEL_STAGE)) {
+        // long horizon: one warp per LP, everything in a global workspace owned by the handle
+        const int P = (T->sp.T + 31) / 32;
+        const size_t per_warp = (size_t)stage2long::NW * P * 32 * sizeof(double);
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dsp_ipm_stage2_long_kernel, 32 * kLongWarps, 0));
+        long long warps = std::min<long long>(N, (long long)T->sm_count * std::max(occ, 1) * kLongWarps);
+        while (warps > 1 && (size_t)warps * per_warp > ((size_t)64 << 30)) warps /= 2;
+        // spread the warps over the SMs: one warp per CTA while there are fewer LPs than SMs x kLongWarps
+        const int wpb = (int)std::min<long long>(kLongWarps, std::max<long long>(1, warps / T->sm_count));
+        const long long blocks = (warps + wpb - 1) / wpb;
+        const size_t need = (size_t)blocks * wpb * per_warp;
+        if (need > T->ws_bytes) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(T->ws);
+            T->ws = nullptr; T->ws_bytes = 0;
+            CK(cudaMalloc((void **)&T->ws, need));
+            T->ws_bytes = need;
+        }
+        stage2long::LongParams LQ;
+        stage2::Params &Q = LQ.q;
+        Q.N = N; Q.cparams = cparams; Q.rparams = rparams; Q.rstride = rparams_stride; Q.Pc = K.Pc; Q.Pr = K.Pr;
+        Q.omap = K.omap; Q.ocmap = K.ocmap; Q.o0 = K.o0;
+        Q.tol = o.tol; Q.feas_tol = o.feas_tol; Q.step_frac = o.step_frac; Q.reg = o.reg_primal; Q.max_iter = o.max_iter;
+        Q.obj = obj; Q.x_out = x; Q.y_out = y; Q.status = status; Q.iters = iters; Q.n = K.n; Q.m = K.m; Q.ticket = ticket;
+        const stagewb::StageParams &S = T->sp;
+        Q.T = S.T; Q.a = S.a; Q.binv = S.binv; Q.hf = S.hf; Q.dl = S.dl; Q.dur = S.dur; Q.krev = S.krev;
+        Q.wcf_off = S.wcf_off; Q.p_off = S.p_off; Q.col_idx = S.col_idx; Q.row_idx = S.row_idx;
+        LQ.ws = T->ws; LQ.P = P;
+        CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
+        dsp_ipm_stage2_long_kernel<<<(unsigned)blocks, 32 * wpb, 0, st>>>(LQ);
+        CK(cudaGetLastError());
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_launches++;
+        g_last_grid = (int)blocks; g_last_block = 32 * wpb; g_last_smem = 0; g_last_ppc = wpb;
+        return 0;
+    }
     if (T->has_stage && (o.kernel == DSP_KERNEL_AUTO || o.kernel == DSP_KERNEL_STAGE)) {
         // generation-2 stage kernel: 32/L LPs per warp, persistent one-warp CTAs, LP groups refill from the ticket counter
         const Stage2Geom g = stage2_geometry(T->sp.T);
@@ -1351,7 +1395,7 @@ static int solve_batch_host_locked(dsp_template *T, int64_t N, const double *cpa
         dstride = K.Pr;
     }
     // templates that run in global-workspace mode share ONE workspace: no concurrent chunk kernels for them
-    const bool ws_template = band_geometry(T, K).ws;
+    const bool ws_template = band_geometry(T, K).ws || (T->has_stage && T->sp.T > kStage2MaxT);    // (the long stage kernel's workspace too)
     const int nchunk = ws_template ? 1 : (int)std::min<int64_t>(in_pinned ? 2 : 8, std::max<int64_t>(1, N / 2048));
     const int64_t per = (N + nchunk - 1) / nchunk;
     for (int c = 0; c < nchunk; ++c) {

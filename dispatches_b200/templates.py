@@ -72,8 +72,8 @@ def wind_battery(T: int, extant_wind: bool = True) -> LPTemplate:
                        iW: 1e-5 * ((0.0 if extant_wind else WIND_CAP_COST) + PA * ann * T * WIND_OP_COST / 8760.0)}))
     B.meta.update(kind="wind_battery", T=T, ann=ann)
     t = B.build()
-    if T <= 96:
-        # stage descriptor for the stage kernels (include/dsp_lp.h: dsp_stage_wb_desc)
+    if True:
+        # stage descriptor for the stage kernels (include/dsp_lp.h: dsp_stage_wb_desc): T <= 96 on chip, longer horizons in a workspace
         cn = {n: j for j, n in enumerate(t.col_names)}
         rn = {n: i for i, n in enumerate(t.row_names)}
         col_idx = [[cn.get(f"blk[{k}].fs.splitter.grid_elec[0]", -1), cn.get(f"blk[{k}].fs.battery.elec_in[0]", -1),

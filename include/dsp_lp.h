@@ -78,7 +78,7 @@ enum { DSP_KERNEL_AUTO = 0, DSP_KERNEL_BAND = 1, DSP_KERNEL_STAGE = 2 /* generat
        DSP_KERNEL_STAGE_V1 = 3 /* generation 1: lane per period, T <= 32 (kept as an independent implementation for tests) */ };
 
 /* Stage descriptor of the wind+battery price-taker flowsheet (wind_battery_LMP.py:172-267, reduced form):
- * T <= 96 periods, per period the columns g,i,o,s,e,p,q and rows r1 (state_evolution, battery.py:145-149),
+ * any T (T <= 96: on chip, several LPs per warp; longer: one warp per LP with its state in a workspace), per period the columns g,i,o,s,e,p,q and rows r1 (state_evolution, battery.py:145-149),
  * r2 (accumulate_energy_throughput :151-153), r3 (state_of_charge_bounds :155-157, slack p),
  * r4 (wind_power.py:120-122 + splitter, slack q).  Lets dsp_lp_solve_batch run the stage kernels (several LPs per warp,
  * iterate in registers, partitioned block elimination: csrc/dsp_stage2.cuh) instead of the generic band kernel; results

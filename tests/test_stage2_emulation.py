@@ -107,3 +107,25 @@ def test_edge_cases(emu):
     assert obj.size == 0
     obj, status, _, _, _ = emu.solve(t, lmp[:1], rp, 8, 3)
     assert status[0] == 0
+
+
+@pytest.mark.parametrize("T", [97, 168, 672])
+def test_long_horizon_variant(emu, T):
+    """dsp_stage2_long.cuh (T > 96: one warp per LP, ceil(T / 32) periods per lane, iterate and temporaries in a workspace):
+    the same algorithm with rolled period loops -- against the oracle, with sizes and capacity factors batched."""
+    t = TP.wind_battery(T)
+    p = SC.pool()
+    rng = np.random.default_rng(T)
+    N = 3
+    starts = rng.integers(0, 8736 - T, N)
+    lmp = np.stack([p["dalmp_303"][s:s + T] for s in starts]) * rng.lognormal(0, 0.25, (N, T))
+    cfs = np.stack([p["dacf_303"][s:s + T] for s in starts])
+    wind, batt = rng.uniform(200, 1600, N), rng.uniform(10, 800, N)
+    rp = TP.wind_battery_rparams(T, cfs, wind, batt)
+    obj, status, iters, x, y = emu.solve_long(t, lmp, rp, warps=2)
+    assert (status == 0).all()
+    ref = np.array([H.solve(L.wind_battery_raw(lmp[i], cfs[i], wind[i], batt[i]))[0] for i in range(N)])
+    assert rel_err(obj, ref).max() < 1e-7
+    c, b, u, k = t.instantiate(lmp[0], rp[0])
+    assert np.abs(t.A @ x[0] - b).max() <= 1e-7 * np.abs(b).max()
+    assert obj[0] == pytest.approx(c @ x[0] + k, rel=1e-9, abs=1e-9)
