@@ -10,6 +10,11 @@
 // periods locally (all lanes busy, P sequential steps), the 32 separators form a chain eliminated from both ends with shuffles
 // (16 steps).  Same algorithm, scaling, start point and stopping rules as the other two wind+battery kernels; period loops are rolled
 // (the code is small), the per-period formulas are those of dsp_stage2.cuh.
+// One numerical difference, measured: with explicitly inverted 2x2 pivot blocks (adjugate / determinant, fine for T <= 96 where
+// the iteration counts are identical to the band kernel's) the iteration count grows with the chunk length -- 42 vs 29 at T = 2184,
+// no convergence at T = 8736: block LDL' with inverted pivots is only conditionally stable and the blocks reach cond 1e12 here.
+// The elimination below is therefore SCALAR (two pivots per period: u1, then u2 -- a Cholesky order, unconditionally backward
+// stable); the stored multipliers replace K, G, H one for one.
 #pragma once
 #include "dsp_stage2.cuh"
 
@@ -28,9 +33,9 @@ enum { W_X = 0,        // 7: xg xi xo xs xe xp xq
        W_PR = 40,      // 9
        W_D = 49,       // 3: diagonal block of the reduced system
        W_F = 52,       // 2: right-hand side / forward-eliminated right-hand side / solution dy
-       W_K = 54,       // 3: inverse of the eliminated block
-       W_G = 57,       // 4: multiplier towards the next period
-       W_H = 61,       // 4: multiplier towards the left separator
+       W_K = 54,       // 3: pivots of the eliminated period (1/a, l = b/a, 1/(c - l b))
+       W_G = 57,       // 4: scalar multipliers towards the next period (two per pivot)
+       W_H = 61,       // 4: scalar multipliers towards the left separator
        NW = 65 };
 
 struct LongParams {
@@ -209,9 +214,9 @@ __device__ int solve_long(const LongParams &LQ, double *wsw, long long p, int la
         }
 
         // =========================================================================================== factorisation (+ forward part of the predictor solve)
-        Mat2 Wc, Mout, Mout2, Cin;
-        Sym2 Asep, Ainv;
-        double g1, g2;
+        Mat2 Wc, Mout, Mout2, Cin;       // Mout / Mout2 + mo4 / mo24: the five multipliers (l, m1a, m1b, m2a, m2b) of a separator elimination
+        Sym2 Asep, Ainv;                 // Ainv: (1/a, l, 1/c') of the separator's final pivot block
+        double g1, g2, mo4 = 0.0, mo24 = 0.0;
         int fo, bo, fsrc, bsrc;
         const bool is_root = (lane == r_root);
         {
@@ -225,25 +230,41 @@ __device__ int solve_long(const LongParams &LQ, double *wsw, long long p, int la
             Sym2 Dc; Dc.a = WS(W_D + 0, 0); Dc.b = WS(W_D + 1, 0); Dc.c = WS(W_D + 2, 0);
             double fa = WS(W_F + 0, 0), fb = WS(W_F + 1, 0);
             for (int j = 0; j < P - 1; ++j) {
-                const Sym2 Kj = inv_spd(Dc);
                 const Scal sc = LSCAL(j);
-                Mat2 C;
                 const bool cn = HAS_S(j);
-                C.a = cn ? -sc.s11 : 0.0; C.d = cn ? -sc.s22 : 0.0; C.b = cn ? sc.s12 : 0.0; C.c = C.b;
-                const Mat2 G = mul_ms(C, Kj);
+                // coupling (next period, this period): symmetric 2x2, entries [k][m] = equation (next, k), unknown (this, m)
+                const double Ca = cn ? -sc.s11 : 0.0, Cb = cn ? sc.s12 : 0.0, Cd = cn ? -sc.s22 : 0.0;
                 Sym2 Dn; Dn.a = WS(W_D + 0, j + 1); Dn.b = WS(W_D + 1, j + 1); Dn.c = WS(W_D + 2, j + 1);
-                sub_xct(Dn, G, C);
-                const Mat2 Hm = mul_ms(transp(E), Kj);
-                sub_xct(dS, Hm, transp(E));
-                dg1 -= fma(Hm.a, fa, Hm.b * fb); dg2 -= fma(Hm.c, fa, Hm.d * fb);
-                const double fna = WS(W_F + 0, j + 1) - fma(G.a, fa, G.b * fb), fnb = WS(W_F + 1, j + 1) - fma(G.c, fa, G.d * fb);
-                const Mat2 GE = mul_mm(G, E);
-                WS(W_K + 0, j) = Kj.a; WS(W_K + 1, j) = Kj.b; WS(W_K + 2, j) = Kj.c;
-                WS(W_G + 0, j) = G.a; WS(W_G + 1, j) = G.b; WS(W_G + 2, j) = G.c; WS(W_G + 3, j) = G.d;
-                WS(W_H + 0, j) = Hm.a; WS(W_H + 1, j) = Hm.b; WS(W_H + 2, j) = Hm.c; WS(W_H + 3, j) = Hm.d;
-                WS(W_F + 0, j) = fa; WS(W_F + 1, j) = fb;
-                E.a = -GE.a; E.b = -GE.b; E.c = -GE.c; E.d = -GE.d;
-                Dc = Dn; fa = fna; fb = fnb;
+                double fn1 = WS(W_F + 0, j + 1), fn2 = WS(W_F + 1, j + 1);
+                // ---- pivot 1: unknown u1 of this period
+                const double i1 = frcp(Dc.a);
+                const double l = Dc.b * i1;
+                const double mn1 = Ca * i1, mn2 = Cb * i1;                 // column 0 of C over the pivot
+                const double ms1 = E.a * i1, ms2 = E.b * i1;               // row 0 of E (= column 0 of the (separator, this) block)
+                const double c2 = fma(-l, Dc.b, Dc.c);
+                const double Cb1 = fma(-mn1, Dc.b, Cb), Cd1 = fma(-mn2, Dc.b, Cd);     // column 1 of C after the first elimination
+                const double Ec1 = fma(-ms1, Dc.b, E.c), Ed1 = fma(-ms2, Dc.b, E.d);   // row 1 of E after it
+                Dn.a = fma(-mn1, Ca, Dn.a); Dn.b = fma(-mn1, Cb, Dn.b); Dn.c = fma(-mn2, Cb, Dn.c);
+                dS.a = fma(-ms1, E.a, dS.a); dS.b = fma(-ms1, E.b, dS.b); dS.c = fma(-ms2, E.b, dS.c);
+                Mat2 En;                                                    // fill (next period, separator)
+                En.a = -Ca * ms1; En.b = -Ca * ms2; En.c = -Cb * ms1; En.d = -Cb * ms2;
+                const double fb1 = fma(-l, fa, fb);
+                fn1 = fma(-mn1, fa, fn1); fn2 = fma(-mn2, fa, fn2);
+                dg1 = fma(-ms1, fa, dg1); dg2 = fma(-ms2, fa, dg2);
+                // ---- pivot 2: unknown u2
+                const double i2 = frcp(c2);
+                const double mq1 = Cb1 * i2, mq2 = Cd1 * i2;
+                const double mt1 = Ec1 * i2, mt2 = Ed1 * i2;
+                Dn.a = fma(-mq1, Cb1, Dn.a); Dn.b = fma(-mq1, Cd1, Dn.b); Dn.c = fma(-mq2, Cd1, Dn.c);
+                dS.a = fma(-mt1, Ec1, dS.a); dS.b = fma(-mt1, Ed1, dS.b); dS.c = fma(-mt2, Ed1, dS.c);
+                En.a = fma(-Cb1, mt1, En.a); En.b = fma(-Cb1, mt2, En.b); En.c = fma(-Cd1, mt1, En.c); En.d = fma(-Cd1, mt2, En.d);
+                fn1 = fma(-mq1, fb1, fn1); fn2 = fma(-mq2, fb1, fn2);
+                dg1 = fma(-mt1, fb1, dg1); dg2 = fma(-mt2, fb1, dg2);
+                WS(W_K + 0, j) = i1; WS(W_K + 1, j) = l; WS(W_K + 2, j) = i2;
+                WS(W_G + 0, j) = mn1; WS(W_G + 1, j) = mn2; WS(W_G + 2, j) = mq1; WS(W_G + 3, j) = mq2;
+                WS(W_H + 0, j) = ms1; WS(W_H + 1, j) = ms2; WS(W_H + 2, j) = mt1; WS(W_H + 3, j) = mt2;
+                WS(W_F + 0, j) = fa; WS(W_F + 1, j) = fb1;
+                E = En; Dc = Dn; fa = fn1; fb = fn2;
             }
             Wc = E; Asep = Dc; g1 = fa; g2 = fb;
             Asep.a += gdown1<L>(dS.a, lane); Asep.b += gdown1<L>(dS.b, lane); Asep.c += gdown1<L>(dS.c, lane);
@@ -257,17 +278,27 @@ __device__ int solve_long(const LongParams &LQ, double *wsw, long long p, int la
             bo = is_root ? (1 << 20) : (low ? r_root - lane : lane - r_root);
             const Mat2 Cout = low ? Wc : transp(Wn);
             Cin = low ? transp(Wn) : Wc;
-            Mout.a = Mout.b = Mout.c = Mout.d = 0.0; Mout2 = Mout;
+            // eliminating a neighbouring separator R (right-hand side q) from this one through the coupling Co (rows: this, columns: R):
+            // two scalar pivots; the multipliers (l, m1a, m1b, m2a, m2b) are kept for the corrector's forward solve
+#define SEP_ELIM(Co, R, q1, q2, M)                                                                    \
+            {                                                                                         \
+                const double i1_ = frcp(R.a), l_ = R.b * i1_;                                         \
+                const double m1a = Co.a * i1_, m1b = Co.c * i1_;                                      \
+                const double c2_ = fma(-l_, R.b, R.c);                                                \
+                const double ka_ = fma(-m1a, R.b, Co.b), kb_ = fma(-m1b, R.b, Co.d);                  \
+                const double i2_ = frcp(c2_);                                                         \
+                const double m2a = ka_ * i2_, m2b = kb_ * i2_;                                        \
+                Asep.a -= fma(m1a, Co.a, m2a * ka_); Asep.b -= fma(m1a, Co.c, m2a * kb_); Asep.c -= fma(m1b, Co.c, m2b * kb_); \
+                const double q2_ = fma(-l_, q1, q2);                                                  \
+                g1 -= fma(m1a, q1, m2a * q2_); g2 -= fma(m1b, q1, m2b * q2_);                         \
+                M[0] = l_; M[1] = m1a; M[2] = m1b; M[3] = m2a; M[4] = m2b;                            \
+            }
+            double Mo[5] = {0, 0, 0, 0, 0}, Mo2[5] = {0, 0, 0, 0, 0};
             for (int k = 1; k <= kmax; ++k) {
                 Sym2 R;
                 R.a = gfrom<L>(Asep.a, fsrc); R.b = gfrom<L>(Asep.b, fsrc); R.c = gfrom<L>(Asep.c, fsrc);
                 const double q1 = gfrom<L>(g1, fsrc), q2 = gfrom<L>(g2, fsrc);
-                if (fo == k) {
-                    const Mat2 X = mul_ms(Cout, inv_spd(R));
-                    sub_xct(Asep, X, Cout);
-                    g1 -= fma(X.a, q1, X.b * q2); g2 -= fma(X.c, q1, X.d * q2);
-                    Mout = X;
-                }
+                if (fo == k) SEP_ELIM(Cout, R, q1, q2, Mo)
             }
             {
                 constexpr int la = r_root - 1, lb = r_root + 1;
@@ -276,38 +307,41 @@ __device__ int solve_long(const LongParams &LQ, double *wsw, long long p, int la
                 Rb.a = gfrom<L>(Asep.a, lb); Rb.b = gfrom<L>(Asep.b, lb); Rb.c = gfrom<L>(Asep.c, lb);
                 const double a1 = gfrom<L>(g1, la), a2 = gfrom<L>(g2, la), b1 = gfrom<L>(g1, lb), b2 = gfrom<L>(g2, lb);
                 if (is_root) {
-                    Mout = mul_ms(Wc, inv_spd(Ra)); sub_xct(Asep, Mout, Wc);
-                    g1 -= fma(Mout.a, a1, Mout.b * a2); g2 -= fma(Mout.c, a1, Mout.d * a2);
+                    SEP_ELIM(Wc, Ra, a1, a2, Mo)
                     const Mat2 Wt = transp(Wn);
-                    Mout2 = mul_ms(Wt, inv_spd(Rb)); sub_xct(Asep, Mout2, Wt);
-                    g1 -= fma(Mout2.a, b1, Mout2.b * b2); g2 -= fma(Mout2.c, b1, Mout2.d * b2);
+                    SEP_ELIM(Wt, Rb, b1, b2, Mo2)
                 }
             }
-            Ainv = inv_spd(Asep);
+#undef SEP_ELIM
+            // the final pivot block of every separator, as scalar pivots too
+            Ainv.a = frcp(Asep.a); Ainv.b = Asep.b * Ainv.a; Ainv.c = frcp(fma(-Ainv.b, Asep.b, Asep.c));     // (1/a, l, 1/c')
+            Mout.a = Mo[0]; Mout.b = Mo[1]; Mout.c = Mo[2]; Mout.d = Mo[3]; Mout2.a = Mo2[0]; Mout2.b = Mo2[1]; Mout2.c = Mo2[2]; Mout2.d = Mo2[3];
+            mo4 = Mo[4]; mo24 = Mo2[4];
         }
         // separator back substitution + local back substitution; the solution dy overwrites W_F
+#define SEP_SOLVE(t1, t2, o1, o2) { const double t2_ = fma(-Ainv.b, (t1), (t2)); o2 = t2_ * Ainv.c; o1 = fma((t1), Ainv.a, -Ainv.b * o2); }
 #define BACK_ALL()                                                                                    \
         {                                                                                             \
             double u1 = 0.0, u2 = 0.0;                                                                \
-            if (is_root) { u1 = fma(Ainv.a, g1, Ainv.b * g2); u2 = fma(Ainv.b, g1, Ainv.c * g2); }    \
+            if (is_root) SEP_SOLVE(g1, g2, u1, u2)                                                    \
             for (int s = 1; s <= smax; ++s) {                                                         \
                 const double r1 = gfrom<L>(u1, bsrc), r2 = gfrom<L>(u2, bsrc);                        \
                 if (bo == s) {                                                                        \
                     const double t1 = g1 - fma(Cin.a, r1, Cin.b * r2);                                \
                     const double t2 = g2 - fma(Cin.c, r1, Cin.d * r2);                                \
-                    u1 = fma(Ainv.a, t1, Ainv.b * t2); u2 = fma(Ainv.b, t1, Ainv.c * t2);             \
+                    SEP_SOLVE(t1, t2, u1, u2)                                                         \
                 }                                                                                     \
             }                                                                                         \
             const double ul1 = gup1<L>(u1, lane), ul2 = gup1<L>(u2, lane);                            \
             double n1 = u1, n2 = u2;                                                                  \
             WS(W_F + 0, P - 1) = u1; WS(W_F + 1, P - 1) = u2;                                         \
             for (int j = P - 2; j >= 0; --j) {                                                        \
-                const double ka = WS(W_K + 0, j), kb = WS(W_K + 1, j), kc_ = WS(W_K + 2, j);          \
-                const double ga = WS(W_G + 0, j), gb = WS(W_G + 1, j), gc = WS(W_G + 2, j), gd = WS(W_G + 3, j); \
-                const double ha = WS(W_H + 0, j), hb = WS(W_H + 1, j), hc = WS(W_H + 2, j), hd = WS(W_H + 3, j); \
+                const double i1 = WS(W_K + 0, j), l = WS(W_K + 1, j), i2 = WS(W_K + 2, j);            \
+                const double mn1 = WS(W_G + 0, j), mn2 = WS(W_G + 1, j), mq1 = WS(W_G + 2, j), mq2 = WS(W_G + 3, j); \
+                const double ms1 = WS(W_H + 0, j), ms2 = WS(W_H + 1, j), mt1 = WS(W_H + 2, j), mt2 = WS(W_H + 3, j); \
                 const double e1 = WS(W_F + 0, j), e2 = WS(W_F + 1, j);                                \
-                const double v1 = fma(ka, e1, kb * e2) - fma(ga, n1, gc * n2) - fma(ha, ul1, hc * ul2);  \
-                const double v2 = fma(kb, e1, kc_ * e2) - fma(gb, n1, gd * n2) - fma(hb, ul1, hd * ul2); \
+                const double v2 = e2 * i2 - fma(mq1, n1, mq2 * n2) - fma(mt1, ul1, mt2 * ul2);        \
+                const double v1 = e1 * i1 - l * v2 - fma(mn1, n1, mn2 * n2) - fma(ms1, ul1, ms2 * ul2); \
                 WS(W_F + 0, j) = v1; WS(W_F + 1, j) = v2;                                             \
                 n1 = v1; n2 = v2;                                                                     \
             }                                                                                         \
@@ -420,26 +454,31 @@ __device__ int solve_long(const LongParams &LQ, double *wsw, long long p, int la
             (void)fpa; (void)fpb; (void)f1_0; (void)f2_0;
             double fa = WS(W_F + 0, 0), fb = WS(W_F + 1, 0);
             for (int j = 0; j < P - 1; ++j) {
-                const double ga = WS(W_G + 0, j), gb = WS(W_G + 1, j), gc = WS(W_G + 2, j), gd = WS(W_G + 3, j);
-                const double ha = WS(W_H + 0, j), hb = WS(W_H + 1, j), hc = WS(W_H + 2, j), hd = WS(W_H + 3, j);
-                dg1 -= fma(ha, fa, hb * fb); dg2 -= fma(hc, fa, hd * fb);
-                const double fna = WS(W_F + 0, j + 1) - fma(ga, fa, gb * fb), fnb = WS(W_F + 1, j + 1) - fma(gc, fa, gd * fb);
-                WS(W_F + 0, j) = fa; WS(W_F + 1, j) = fb;
+                const double l = WS(W_K + 1, j);
+                const double mn1 = WS(W_G + 0, j), mn2 = WS(W_G + 1, j), mq1 = WS(W_G + 2, j), mq2 = WS(W_G + 3, j);
+                const double ms1 = WS(W_H + 0, j), ms2 = WS(W_H + 1, j), mt1 = WS(W_H + 2, j), mt2 = WS(W_H + 3, j);
+                const double fb1 = fma(-l, fa, fb);
+                dg1 -= fma(ms1, fa, mt1 * fb1); dg2 -= fma(ms2, fa, mt2 * fb1);
+                const double fna = WS(W_F + 0, j + 1) - fma(mn1, fa, mq1 * fb1), fnb = WS(W_F + 1, j + 1) - fma(mn2, fa, mq2 * fb1);
+                WS(W_F + 0, j) = fa; WS(W_F + 1, j) = fb1;
                 fa = fna; fb = fnb;
             }
             g1 = fa + gdown1<L>(dg1, lane); g2 = fb + gdown1<L>(dg2, lane);
+            // separator forward solve with the stored multipliers (l, m1a, m1b, m2a, m2b)
+#define SEP_FWD(M, m4, q1, q2) { const double q2_ = fma(-M.a, (q1), (q2)); g1 -= fma(M.b, (q1), M.d * q2_); g2 -= fma(M.c, (q1), (m4) * q2_); }
             for (int k = 1; k <= kmax; ++k) {
                 const double q1 = gfrom<L>(g1, fsrc), q2 = gfrom<L>(g2, fsrc);
-                if (fo == k) { g1 -= fma(Mout.a, q1, Mout.b * q2); g2 -= fma(Mout.c, q1, Mout.d * q2); }
+                if (fo == k) SEP_FWD(Mout, mo4, q1, q2)
             }
             {
                 constexpr int la = r_root - 1, lb = r_root + 1;
                 const double a1 = gfrom<L>(g1, la), a2 = gfrom<L>(g2, la), b1 = gfrom<L>(g1, lb), b2 = gfrom<L>(g2, lb);
                 if (is_root) {
-                    g1 -= fma(Mout.a, a1, Mout.b * a2); g2 -= fma(Mout.c, a1, Mout.d * a2);
-                    g1 -= fma(Mout2.a, b1, Mout2.b * b2); g2 -= fma(Mout2.c, b1, Mout2.d * b2);
+                    SEP_FWD(Mout, mo4, a1, a2)
+                    SEP_FWD(Mout2, mo24, b1, b2)
                 }
             }
+#undef SEP_FWD
         }
         BACK_ALL();
 
@@ -565,6 +604,7 @@ __device__ int solve_long(const LongParams &LQ, double *wsw, long long p, int la
 #undef Y1N
 #undef Y2N
 #undef BACK_ALL
+#undef SEP_SOLVE
 }
 
 // persistent warps: one LP at a time per warp, tickets from a global counter; second attempt as in the other kernels
