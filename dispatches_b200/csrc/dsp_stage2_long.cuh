@@ -206,6 +206,9 @@ __device__ int solve_long(const LongParams &LQ, double *wsw, long long p, int la
         {
             const double den = dmax(kGapFloor2, fabs(po));
             const double gap = fabs(po - dob) / den, cgap = ntot * mu / den;
+#if !defined(__CUDA_ARCH__) && defined(DSP_EMU_TRACE)
+            if (lane == 0) printf("it %2d  res %.2e (p %.2e d %.2e)  gap %.2e  cgap %.2e  mu %.2e\n", it, res, gmax<1>(pm) / nrm_b, dm / nrm_c, gap, cgap, mu);
+#endif
             if (!(mu == mu) || !(po == po) || mu > 1e100) { status = DSP_NUMERICAL; break; }
             if (res < Q.feas_tol && gap < Q.tol) { status = DSP_OPTIMAL; break; }
             if (cgap < Q.tol && res < 10.0 * Q.feas_tol && gap < 10.0 * Q.tol) { status = DSP_OPTIMAL; break; }
