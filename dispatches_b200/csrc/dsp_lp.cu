@@ -75,6 +75,7 @@ struct KParams {
     const double *amap_coef;
     const int *at_from;           // CSC position -> CSR position (A' values follow A's)
     const int *asm_qa, *asm_qb;   // band assembly: the two CSR positions whose product is asm_val[p]
+    int retry_only;               // second pass behind a stage kernel: solve only the LPs whose status is MAX_ITER / NUMERICAL
 };
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -534,6 +535,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) dsp_ipm_band_kernel(const K
         if (lane == 0) t = atomicAdd(P.ticket, 1ULL);
         t = __shfl_sync(0xffffffffu, t, 0);
         if ((long long)t >= P.N) break;
+        if (P.retry_only && (P.status[t] == DSP_OPTIMAL || P.status[t] == DSP_INFEASIBLE)) continue;
         int st, it0 = 0;
         // second attempt (shorter step, stronger proximal term) for the rare LP whose first attempt ends non-optimal
         solve_one<BW>(W, H, P, (long long)t, lane, P.step_frac, P.reg, 0, &st, &it0);
@@ -1100,6 +1102,7 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
     K.tol = o.tol; K.feas_tol = o.feas_tol; K.step_frac = o.step_frac; K.reg = o.reg_primal; K.max_iter = o.max_iter;
     K.obj = obj; K.status = status; K.iters = iters; K.x_out = x; K.y_out = y;
     K.ticket = ticket;
+    K.retry_only = 0;
     if (T->has_stage && T->sp.T > kStage2MaxT && (o.kernel == DSP_KERNEL_AUTO || o.kernel == DSP_KERNEL_STAGE)) {
         // long horizon: one warp per LP, everything in a global workspace owned by the handle
         const int P = (T->sp.T + 31) / 32;
@@ -1132,12 +1135,19 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
         dsp_ipm_stage2_long_kernel<<<(unsigned)blocks, 32 * wpb, 0, st>>>(LQ);
         CK(cudaGetLastError());
-        std::lock_guard<std::mutex> lk(g_mu);
-        g_launches++;
-        g_last_grid = (int)blocks; g_last_block = 32 * wpb; g_last_smem = 0; g_last_ppc = wpb;
-        return 0;
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            g_launches++;
+            g_last_grid = (int)blocks; g_last_block = 32 * wpb; g_last_smem = 0; g_last_ppc = wpb;
+        }
+        // At T = 8736 cond(M) reaches 1e15 and the partitioned elimination order rounds differently from the band kernel's
+        // sequential one: about 1 LP in 60 of the reference's full-year sweep stalls here and converges there
+        // (profiles/long_hard_r2.log).  The band kernel therefore follows on the same stream and re-solves ONLY the LPs this
+        // kernel left with MAX_ITER / NUMERICAL (its warps skip every other ticket: a few microseconds when there is none).
+        if (o.kernel == DSP_KERNEL_STAGE && getenv("DSP_LONG_NO_RETRY")) return 0;       // experiments only
+        K.retry_only = 1;
     }
-    if (T->has_stage && (o.kernel == DSP_KERNEL_AUTO || o.kernel == DSP_KERNEL_STAGE)) {
+    if (!K.retry_only && T->has_stage && (o.kernel == DSP_KERNEL_AUTO || o.kernel == DSP_KERNEL_STAGE)) {
         // generation-2 stage kernel: 32/L LPs per warp, persistent one-warp CTAs, LP groups refill from the ticket counter
         const Stage2Geom g = stage2_geometry(T->sp.T);
         const int per_warp = 32 / g.L;
@@ -1170,7 +1180,7 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         g_last_grid = (int)blocks; g_last_block = 32 * wpb; g_last_smem = (int)smem; g_last_ppc = per_warp * wpb;
         return 0;
     }
-    if (T->has_stage && o.kernel == DSP_KERNEL_STAGE_V1) {
+    if (!K.retry_only && T->has_stage && o.kernel == DSP_KERNEL_STAGE_V1) {
         if (T->sp.T > 32) { g_err = "dsp_lp_solve_batch: the lane-per-period stage kernel needs T <= 32"; return DSP_E_ARG; }
         // generation-1 stage kernel (lane per period): no shared memory; persistent warps, one LP per warp at a time
         const int wpb = DSP_STAGE_WPB;
@@ -1185,7 +1195,7 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         g_last_grid = (int)blocks; g_last_block = wpb * 32; g_last_smem = 0; g_last_ppc = wpb;
         return 0;
     }
-    if (T->has_chain1 && (o.kernel == DSP_KERNEL_AUTO || o.kernel == DSP_KERNEL_STAGE)) {
+    if (!K.retry_only && T->has_chain1 && (o.kernel == DSP_KERNEL_AUTO || o.kernel == DSP_KERNEL_STAGE)) {
         const int L = chain1_lanes(T->c1_T), per_warp = 32 / L, NF = T->c1_NF;
         int wmax = kChain1Warps;
         if (const char *e = getenv("DSP_STAGE2_WARPS")) wmax = std::min(kChain1Warps, std::max(1, atoi(e)));
@@ -1213,7 +1223,7 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         g_last_grid = (int)blocks; g_last_block = 32 * wpb; g_last_smem = (int)smem; g_last_ppc = per_warp * wpb;
         return 0;
     }
-    if (o.kernel == DSP_KERNEL_STAGE || o.kernel == DSP_KERNEL_STAGE_V1) {
+    if (!K.retry_only && (o.kernel == DSP_KERNEL_STAGE || o.kernel == DSP_KERNEL_STAGE_V1)) {
         g_err = "dsp_lp_solve_batch: the template has no stage descriptor";
         return DSP_E_ARG;
     }

@@ -146,6 +146,9 @@ struct Per {            // one period of the iterate + its data (registers)
     double si, so, wi, wo;
     double y1, y2, y3, y4;
 };
+S2D double comp_sum(const Per &q) {           // sum of the 9 complementarity products of a period
+    return q.xg * q.zg + q.xi * q.zi + q.xo * q.zo + q.xs * q.zs + q.xe * q.ze + q.xp * q.zp + q.xq * q.zq + q.si * q.wi + q.so * q.wo;
+}
 struct Res { double rp1, rp2, rp3, rp4, rdg, rdi, rdo, rds, rde, rdp, rdq, rui, ruo; };
 struct H7 { double hg, hi, ho, hs, he, hp, hq; };
 struct Cst { double a, binv, hf, dl; };
@@ -250,7 +253,94 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
     int it = 0, it0 = 0, attempt = 0, Tg = 0;
     int mode = 1;                     // 0 running, 1 needs a new LP, 2 retries its LP with safer parameters, 3 out of work
 
+    double mu_keep = 0.0;             // complementarity measure of the group's current iterate (set by the check / the refill)
+    double xs_left = 0.0, xe_left = 0.0, y1_right = 0.0, y2_right = 0.0;      // neighbours of the lane's block
+#define XSP(j) ((j) == 0 ? xs_left : pr[(j) > 0 ? (j) - 1 : 0].xs)
+#define XEP(j) ((j) == 0 ? xe_left : pr[(j) > 0 ? (j) - 1 : 0].xe)
+#define Y1N(j) ((j) == P - 1 ? y1_right : pr[(j) < P - 1 ? (j) + 1 : 0].y1)
+#define Y2N(j) ((j) == P - 1 ? y2_right : pr[(j) < P - 1 ? (j) + 1 : 0].y2)
+#define ACT(j) (gl * P + (j) < Tg)
+#define HAS_S(j) (gl * P + (j) < Tg - 1)
+#define NEIGHBOURS()                                                                                      \
+    {                                                                                                     \
+        xs_left = gup1<L>(pr[P - 1].xs, gl); xe_left = gup1<L>(pr[P - 1].xe, gl);                        \
+        y1_right = gdown1<L>(pr[0].y1, gl); y2_right = gdown1<L>(pr[0].y2, gl);                          \
+    }
+
     for (;;) {
+        // =========================================================================================== convergence check
+        // residual norms, duality gap and complementarity of the iterate every running group holds (one cheap evaluation of the
+        // residuals).  It runs BEFORE the refill, so a group whose LP has just converged starts its next LP in this very round
+        // (until round 2 the test sat inside pass 1 and a finished group idled through the rest of that round: 1 round in 13)
+        if (__any_sync(FULL, mode == 0)) {
+            NEIGHBOURS();
+            double pm = 0.0, dm = 0.0, mus = 0.0, po = 0.0, dob = 0.0;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const Per &q = pr[j];
+                if (ACT(j)) {
+                    Res r;
+                    residuals(q, SMF(A_C, j), SMF(A_B4, j), XSP(j), XEP(j), Y1N(j), Y2N(j), b3, u, K, true, HAS_S(j), r);
+                    pm = dmax(pm, dmax(dmax(dmax(fabs(r.rp1), fabs(r.rp2)), dmax(fabs(r.rp3), fabs(r.rp4))), dmax(fabs(r.rui), fabs(r.ruo))));
+                    dm = dmax(dm, dmax(dmax(dmax(fabs(r.rdg), fabs(r.rdi)), dmax(fabs(r.rdo), fabs(r.rds))),
+                                       dmax(dmax(fabs(r.rde), fabs(r.rdp)), fabs(r.rdq))));
+                    mus += comp_sum(q);
+                    po += SMF(A_C, j) * (q.xg + q.xo);
+                    dob += b3 * q.y3 + SMF(A_B4, j) * q.y4 - u * (q.wi + q.wo);
+                }
+            }
+            const double res = gmax<L>(dmax(pm / nrm_b, dm / nrm_c));
+            mus = gsum<L>(mus); po = gsum<L>(po); dob = gsum<L>(dob);
+            const double mu = mus / ntot;
+            const double den = dmax(kGapFloor2, fabs(po));
+            const double gap = fabs(po - dob) / den, cgap = ntot * mu / den;
+            if (mode == 0) {
+                mu_keep = mu;
+                int status = -1;
+                if (!(mu == mu) || !(po == po) || mu > 1e100) status = DSP_NUMERICAL;
+                else if (res < Q.feas_tol && gap < Q.tol) status = DSP_OPTIMAL;
+                else if (cgap < Q.tol && res < 10.0 * Q.feas_tol && gap < 10.0 * Q.tol) status = DSP_OPTIMAL;
+                else if (cgap < 1e-3 * Q.tol) status = (res < 100.0 * Q.feas_tol && gap < 1000.0 * Q.tol) ? DSP_OPTIMAL : DSP_NUMERICAL;
+                else if (it == Q.max_iter) status = DSP_MAX_ITER;
+                if (status >= 0) {
+                    if (gl == 0) {
+                        Q.obj[p] = po * beta_b * beta_c + kconst;
+                        Q.status[p] = status;
+                        Q.iters[p] = it + it0;
+                    }
+                    if (Q.x_out) {
+                        double *xo_ = Q.x_out + p * (long long)Q.n;
+#pragma unroll
+                        for (int j = 0; j < P; ++j) {
+                            const int t = gl * P + j;
+                            if (t < T) {
+                                const int *ci_ = Q.col_idx + t * 7;
+                                const Per &q = pr[j];
+                                const double vals[7] = {q.xg, q.xi, q.xo, q.xs, q.xe, q.xp, q.xq};
+#pragma unroll
+                                for (int k = 0; k < 7; ++k)
+                                    if (ci_[k] >= 0) xo_[ci_[k]] = vals[k] * beta_b;
+                            }
+                        }
+                    }
+                    if (Q.y_out) {
+                        double *yo_ = Q.y_out + p * (long long)Q.m;
+#pragma unroll
+                        for (int j = 0; j < P; ++j) {
+                            const int t = gl * P + j;
+                            if (t < T) {
+                                const int *ri_ = Q.row_idx + t * 4;
+                                yo_[ri_[0]] = pr[j].y1 * beta_c; yo_[ri_[1]] = pr[j].y2 * beta_c;
+                                yo_[ri_[2]] = pr[j].y3 * beta_c; yo_[ri_[3]] = pr[j].y4 * beta_c;
+                            }
+                        }
+                    }
+                    // second attempt (shorter step, stronger proximal term) for the rare LP whose first attempt ends non-optimal
+                    if (status != DSP_OPTIMAL && attempt == 0) { mode = 2; attempt = 1; it0 = it + it0; }
+                    else mode = 1;
+                }
+            }
+        }
         // =========================================================================================== (re)fill groups
         if (__any_sync(FULL, mode == 1 || mode == 2)) {
             unsigned long long tk = 0;
@@ -281,11 +371,19 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
             kc = gsum<L>(kc);
             b4m = gmax<L>(b4m);
             cm = gmax<L>(cm);
+            double mu0 = 0.0;
             if (ld) {
                 kconst = kc + Q.o0;
                 if (Pw < 0.0) {       // negative battery power bound: infeasible (not silently clamped)
                     if (gl == 0) { Q.obj[p] = __longlong_as_double(0x7ff8000000000000LL); Q.status[p] = DSP_INFEASIBLE; Q.iters[p] = 0; }
                     mode = 1; Tg = 0;                      // fetches the next LP at the top of the next round
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {           // (an all-inactive group must not carry the finished LP's iterate)
+                        Per &q = pr[j];
+                        q.xg = q.xi = q.xo = q.xs = q.xe = q.xp = q.xq = 0.0;
+                        q.zg = q.zi = q.zo = q.zs = q.ze = q.zp = q.zq = 0.0;
+                        q.si = q.so = q.wi = q.wo = q.y1 = q.y2 = q.y3 = q.y4 = 0.0;
+                    }
                 } else {
                     step_frac = attempt ? 0.99 : Q.step_frac;
                     reg = attempt ? 10.0 * Q.reg : Q.reg;
@@ -311,11 +409,14 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
                         q.zg = one; q.zi = one; q.zo = one; q.zs = has_s ? 1.0 : 0.0; q.ze = one; q.zp = one; q.zq = one;
                         q.si = act ? u - x0 : 0.0; q.so = q.si; q.wi = one; q.wo = one;
                         q.y1 = q.y2 = q.y3 = q.y4 = 0.0;
+                        if (act) mu0 += comp_sum(q);
                     }
                     it = 0;
                     mode = 0;
                 }
             }
+            mu0 = gsum<L>(mu0);
+            if (ld) mu_keep = mu0 / ntot;      // (the start point is never optimal: its own convergence check is skipped)
         }
         if (cta_all<CTA_SYNC>(mode == 3)) break;
         if (__all_sync(FULL, mode == 3)) {
@@ -328,20 +429,12 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
         }
 
         // =========================================================================================== neighbours of the lane's block
-        const double xs_left = gup1<L>(pr[P - 1].xs, gl), xe_left = gup1<L>(pr[P - 1].xe, gl);
-        const double y1_right = gdown1<L>(pr[0].y1, gl), y2_right = gdown1<L>(pr[0].y2, gl);
-#define XSP(j) ((j) == 0 ? xs_left : pr[(j) > 0 ? (j) - 1 : 0].xs)
-#define XEP(j) ((j) == 0 ? xe_left : pr[(j) > 0 ? (j) - 1 : 0].xe)
-#define Y1N(j) ((j) == P - 1 ? y1_right : pr[(j) < P - 1 ? (j) + 1 : 0].y1)
-#define Y2N(j) ((j) == P - 1 ? y2_right : pr[(j) < P - 1 ? (j) + 1 : 0].y2)
-#define ACT(j) (gl * P + (j) < Tg)
-#define HAS_S(j) (gl * P + (j) < Tg - 1)
+        NEIGHBOURS();
 
         // =========================================================================================== pass 1
-        // residuals + norms, scaling matrix, local elimination of the wind-balance / SoC-bound rows, predictor right-hand side
+        // residuals, scaling matrix, local elimination of the wind-balance / SoC-bound rows, predictor right-hand side
         Sym2 Dd[P];
         double f1[P], f2[P];
-        double pm = 0.0, dm = 0.0, mus = 0.0, po = 0.0, dob = 0.0;
         double s11l, s22l, s12l;       // scaling blocks of the left neighbour's last period
         {
             double s11c = 0.0, s22c = 0.0, s12c = 0.0, ph1c = 0.0, ph2c = 0.0;      // carried from period j-1
@@ -352,13 +445,6 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
                 Res r;
                 residuals(q, SMF(A_C, j), SMF(A_B4, j), XSP(j), XEP(j), Y1N(j), Y2N(j), b3, u, K, act, has_s, r);
                 if (act) {
-                    pm = dmax(pm, dmax(dmax(dmax(fabs(r.rp1), fabs(r.rp2)), dmax(fabs(r.rp3), fabs(r.rp4))), dmax(fabs(r.rui), fabs(r.ruo))));
-                    dm = dmax(dm, dmax(dmax(dmax(fabs(r.rdg), fabs(r.rdi)), dmax(fabs(r.rdo), fabs(r.rds))),
-                                       dmax(dmax(fabs(r.rde), fabs(r.rdp)), fabs(r.rdq))));
-                    mus += q.xg * q.zg + q.xi * q.zi + q.xo * q.zo + q.xs * q.zs + q.xe * q.ze + q.xp * q.zp + q.xq * q.zq
-                           + q.si * q.wi + q.so * q.wo;
-                    po += SMF(A_C, j) * (q.xg + q.xo);
-                    dob += b3 * q.y3 + SMF(A_B4, j) * q.y4 - u * (q.wi + q.wo);
                     // ---- scaling matrix and reciprocals.  d = 1 / (z/x [+ w/s] + reg / max(1, x^2))
                     const double rxg = frcp(q.xg), rxi = frcp(q.xi), rxo = frcp(q.xo), rxe = frcp(q.xe), rxp = frcp(q.xp), rxq = frcp(q.xq);
                     const double rxs = has_s ? frcp(q.xs) : 0.0;
@@ -413,63 +499,7 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
                 f1[0] -= ph1l; f2[0] -= ph2l;
             }
         }
-        // ---- norms, convergence test, results (per group)
-        {
-            const double res = gmax<L>(dmax(pm / nrm_b, dm / nrm_c));
-            mus = gsum<L>(mus); po = gsum<L>(po); dob = gsum<L>(dob);
-            const double mu = mus / ntot;
-            const double den = dmax(kGapFloor2, fabs(po));
-            const double gap = fabs(po - dob) / den, cgap = ntot * mu / den;
-            if (mode == 0) {
-                int status = -1;
-                if (!(mu == mu) || !(po == po) || mu > 1e100) status = DSP_NUMERICAL;
-                else if (res < Q.feas_tol && gap < Q.tol) status = DSP_OPTIMAL;
-                else if (cgap < Q.tol && res < 10.0 * Q.feas_tol && gap < 10.0 * Q.tol) status = DSP_OPTIMAL;
-                else if (cgap < 1e-3 * Q.tol) status = (res < 100.0 * Q.feas_tol && gap < 1000.0 * Q.tol) ? DSP_OPTIMAL : DSP_NUMERICAL;
-                else if (it == Q.max_iter) status = DSP_MAX_ITER;
-                if (status >= 0) {
-                    if (gl == 0) {
-                        Q.obj[p] = po * beta_b * beta_c + kconst;
-                        Q.status[p] = status;
-                        Q.iters[p] = it + it0;
-                    }
-                    if (Q.x_out) {
-                        double *xo_ = Q.x_out + p * (long long)Q.n;
-#pragma unroll
-                        for (int j = 0; j < P; ++j) {
-                            const int t = gl * P + j;
-                            if (t < T) {
-                                const int *ci_ = Q.col_idx + t * 7;
-                                const Per &q = pr[j];
-                                const double vals[7] = {q.xg, q.xi, q.xo, q.xs, q.xe, q.xp, q.xq};
-#pragma unroll
-                                for (int k = 0; k < 7; ++k)
-                                    if (ci_[k] >= 0) xo_[ci_[k]] = vals[k] * beta_b;
-                            }
-                        }
-                    }
-                    if (Q.y_out) {
-                        double *yo_ = Q.y_out + p * (long long)Q.m;
-#pragma unroll
-                        for (int j = 0; j < P; ++j) {
-                            const int t = gl * P + j;
-                            if (t < T) {
-                                const int *ri_ = Q.row_idx + t * 4;
-                                yo_[ri_[0]] = pr[j].y1 * beta_c; yo_[ri_[1]] = pr[j].y2 * beta_c;
-                                yo_[ri_[2]] = pr[j].y3 * beta_c; yo_[ri_[3]] = pr[j].y4 * beta_c;
-                            }
-                        }
-                    }
-                    // second attempt (shorter step, stronger proximal term) for the rare LP whose first attempt ends non-optimal
-                    if (status != DSP_OPTIMAL && attempt == 0) { mode = 2; attempt = 1; it0 = it + it0; }
-                    else mode = 1;
-                }
-            }
-            // the rest of the round runs for every group in lock step; a group that has just finished computes on, its
-            // registers are re-initialised at the top of the next round (all cross-lane traffic stays inside the group)
-            mus = mu;                  // keep mu (per group) for the centring parameter
-        }
-        const double mu = mus;
+        const double mu = mu_keep;
 
         if (DSP_S2_SYNCMASK & 1) cta_sync<CTA_SYNC>();
         // =========================================================================================== factorisation + predictor solve
@@ -831,6 +861,7 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
 #undef Y2N
 #undef ACT
 #undef HAS_S
+#undef NEIGHBOURS
 #undef SEP_BACK
 #undef LOCAL_BACK
 }
