@@ -118,7 +118,111 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
 #define BND(j, c) ((bounded[j] >> (c)) & 1)
 #define ACT(j) (gl * P + (j) < Tg)
 
+    double mu_keep = 0.0;             // complementarity measure of the group's current iterate (set by the check / the refill)
+    const double ntot = ntot_t;
+    double hx_left = 0.0;             // hn * x_state of the left neighbour's last period
+    double y_right = 0.0;             // dual of the right neighbour's first period
+    // state of the previous period enters this period's row; the next period's dual enters this period's state column
+#define NEIGHBOURS()                                                                                   \
+    {                                                                                                  \
+        const double v_ = HAS(P - 1, NF) ? SMF(SM::A_HN, P - 1) * pr[P - 1].x[NF] : 0.0;               \
+        hx_left = gup1<L>(v_, gl);                                                                     \
+        y_right = gdown1<L>(pr[0].y, gl);                                                              \
+    }
+#define YN(j) ((j) == P - 1 ? y_right : pr[(j) < P - 1 ? (j) + 1 : 0].y)
+    // residuals of one period (registers); hxp = hn * x_state of period t-1
+#define RESID(j, hxp)                                                                                  \
+        double rp_ = 0.0, rd_[NC], ru_[NC];                                                            \
+        {                                                                                              \
+            double ax = (hxp);                                                                         \
+            _Pragma("unroll")                                                                          \
+            for (int c = 0; c < NC; ++c) {                                                             \
+                const double a_ = SMF(SM::A_A + c, j);                                                 \
+                ax = fma(a_, q.x[c], ax);                                                              \
+                double r_ = SMF(SM::A_C + c, j) - a_ * q.y - q.z[c];                                   \
+                if (c == NF) r_ -= SMF(SM::A_HN, j) * YN(j);                                           \
+                ru_[c] = 0.0;                                                                          \
+                if (BND(j, c)) { r_ += q.w[c]; ru_[c] = SMF(SM::A_U + c, j) - q.x[c] - q.s[c]; }       \
+                rd_[c] = HAS(j, c) ? r_ : 0.0;                                                         \
+            }                                                                                          \
+            rp_ = SMF(SM::A_B, j) - ax;                                                                \
+        }
+
     for (;;) {
+        // =========================================================================================== convergence check
+        // before the refill (as in dsp_stage2.cuh): a group whose LP has just converged starts its next LP in this very round
+        if (__any_sync(FULL, mode == 0)) {
+            NEIGHBOURS();
+            double pm = 0.0, dm = 0.0, mus = 0.0, po = 0.0, dob = 0.0;
+            double hxc = hx_left;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const Per<NF> &q = pr[j];
+                if (ACT(j)) {
+                    RESID(j, hxc);
+                    pm = dmax(pm, fabs(rp_));
+                    dob += SMF(SM::A_B, j) * q.y;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        if (HAS(j, c)) {
+                            dm = dmax(dm, fabs(rd_[c]));
+                            mus += q.x[c] * q.z[c];
+                            po += SMF(SM::A_C + c, j) * q.x[c];
+                            if (BND(j, c)) {
+                                pm = dmax(pm, fabs(ru_[c]));
+                                mus += q.s[c] * q.w[c];
+                                dob -= SMF(SM::A_U + c, j) * q.w[c];
+                            }
+                        }
+                    }
+                    hxc = SMF(SM::A_HN, j) * q.x[NF];
+                } else {
+                    hxc = 0.0;
+                }
+            }
+            const double res = gmax<L>(dmax(pm / nrm_b, dm / nrm_c));
+            mus = gsum<L>(mus); po = gsum<L>(po); dob = gsum<L>(dob);
+            const double mu = mus / ntot;
+            const double den = dmax(kGapFloor2, fabs(po));
+            const double gap = fabs(po - dob) / den, cgap = ntot * mu / den;
+            if (mode == 0) {
+                mu_keep = mu;
+                int status = -1;
+                if (!(mu == mu) || !(po == po) || mu > 1e100) status = DSP_NUMERICAL;
+                else if (res < Q.feas_tol && gap < Q.tol) status = DSP_OPTIMAL;
+                else if (cgap < Q.tol && res < 10.0 * Q.feas_tol && gap < 10.0 * Q.tol) status = DSP_OPTIMAL;
+                else if (cgap < 1e-3 * Q.tol) status = (res < 100.0 * Q.feas_tol && gap < 1000.0 * Q.tol) ? DSP_OPTIMAL : DSP_NUMERICAL;
+                else if (it == Q.max_iter) status = DSP_MAX_ITER;
+                if (status >= 0) {
+                    if (gl == 0) { Q.obj[p] = po * beta_b * beta_c + kconst; Q.status[p] = status; Q.iters[p] = it + it0; }
+                    if (Q.x_out) {
+                        double *xo_ = Q.x_out + p * (long long)Q.n;
+#pragma unroll
+                        for (int j = 0; j < P; ++j) {
+                            const int t = gl * P + j;
+                            if (t < T) {
+#pragma unroll
+                                for (int c = 0; c < NC; ++c)
+                                    if (HAS(j, c)) {
+                                        const int col = Q.col_idx[t * NC + c];
+                                        xo_[Q.x_perm ? Q.x_perm[col] : col] = pr[j].x[c] * beta_b;
+                                    }
+                            }
+                        }
+                    }
+                    if (Q.y_out) {
+                        double *yo_ = Q.y_out + p * (long long)Q.m;
+#pragma unroll
+                        for (int j = 0; j < P; ++j) {
+                            const int t = gl * P + j;
+                            if (t < T) { const int row = Q.row_idx[t]; yo_[Q.y_perm ? Q.y_perm[row] : row] = pr[j].y * beta_c; }
+                        }
+                    }
+                    if (status != DSP_OPTIMAL && attempt == 0) { mode = 2; attempt = 1; it0 = it + it0; }
+                    else mode = 1;
+                }
+            }
+        }
         // =========================================================================================== (re)fill groups
         if (__any_sync(FULL, mode == 1 || mode == 2)) {
             unsigned long long tk = 0;
@@ -188,10 +292,17 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
                 }
             }
             infl = gmax<L>(infl);               // (collectives stay outside the divergent branches)
+            double mu0 = 0.0;
             if (ld) {
                 if (infl > 0.0) {
                     if (gl == 0) { Q.obj[p] = __longlong_as_double(0x7ff8000000000000LL); Q.status[p] = DSP_INFEASIBLE; Q.iters[p] = it0; }
                     mode = 1; Tg = 0;
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {           // (an all-inactive group must not carry the finished LP's iterate)
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) pr[j].x[c] = pr[j].z[c] = pr[j].s[c] = pr[j].w[c] = 0.0;
+                        pr[j].y = 0.0;
+                    }
                 } else {
                     step_frac = attempt ? 0.99 : Q.step_frac;
                     reg = attempt ? 10.0 * Q.reg : Q.reg;
@@ -214,6 +325,7 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
                                 sj = uj - xj; wj = 1.0;
                             }
                             pr[j].x[c] = xj; pr[j].z[c] = (act && HAS(j, c)) ? 1.0 : 0.0; pr[j].s[c] = sj; pr[j].w[c] = wj;
+                            if (act && HAS(j, c)) { mu0 += pr[j].x[c] * pr[j].z[c]; if (BND(j, c)) mu0 += sj * wj; }
                         }
                     }
                     nrm_b = 1.0 + bsmax;            // completed by the group maximum below
@@ -223,42 +335,17 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
             }
             // (the group maximum of |b| for the residual norm; executed by every lane)
             nrm_b = 1.0 + gmax<L>(nrm_b - 1.0);
+            mu0 = gsum<L>(mu0);
+            if (ld) mu_keep = mu0 / ntot;      // (the start point is never optimal: its own convergence check is skipped)
         }
         if (cta_all<CTA_SYNC>(mode == 3)) break;
         if (__all_sync(FULL, mode == 3)) continue;     // out of work: leave the issue slots to the warps that still iterate
 
         // =========================================================================================== neighbours of the lane's block
-        // state of the previous period enters this period's row; the next period's dual enters this period's state column
-        const double ntot = ntot_t;
-        double hx_left;          // hn * x_state of the left neighbour's last period
-        {
-            const double v = HAS(P - 1, NF) ? SMF(SM::A_HN, P - 1) * pr[P - 1].x[NF] : 0.0;
-            hx_left = gup1<L>(v, gl);
-        }
-        const double y_right = gdown1<L>(pr[0].y, gl);
-#define YN(j) ((j) == P - 1 ? y_right : pr[(j) < P - 1 ? (j) + 1 : 0].y)
-
-        // residuals of one period (registers); hxp = hn * x_state of period t-1
-#define RESID(j, hxp)                                                                                  \
-        double rp_ = 0.0, rd_[NC], ru_[NC];                                                            \
-        {                                                                                              \
-            double ax = (hxp);                                                                         \
-            _Pragma("unroll")                                                                          \
-            for (int c = 0; c < NC; ++c) {                                                             \
-                const double a_ = SMF(SM::A_A + c, j);                                                 \
-                ax = fma(a_, q.x[c], ax);                                                              \
-                double r_ = SMF(SM::A_C + c, j) - a_ * q.y - q.z[c];                                   \
-                if (c == NF) r_ -= SMF(SM::A_HN, j) * YN(j);                                           \
-                ru_[c] = 0.0;                                                                          \
-                if (BND(j, c)) { r_ += q.w[c]; ru_[c] = SMF(SM::A_U + c, j) - q.x[c] - q.s[c]; }       \
-                rd_[c] = HAS(j, c) ? r_ : 0.0;                                                         \
-            }                                                                                          \
-            rp_ = SMF(SM::A_B, j) - ax;                                                                \
-        }
+        NEIGHBOURS();
 
         // =========================================================================================== pass 1
         double Dd[P], f1[P], Cn[P];        // diagonal, right-hand side, coupling with the next period
-        double pm = 0.0, dm = 0.0, mus = 0.0, po = 0.0, dob = 0.0;
         double dl_left, ql_left;           // hn^2 d and hn d h of the left neighbour's last period
         {
             double hxc = hx_left, ddc = 0.0, qqc = 0.0;       // carried from period j-1 (ddc / qqc of the left lane are added after the loop)
@@ -267,8 +354,6 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
                 const Per<NF> &q = pr[j];
                 if (ACT(j)) {
                     RESID(j, hxc);
-                    pm = dmax(pm, fabs(rp_));
-                    dob += SMF(SM::A_B, j) * q.y;
                     double diag = ddc, rhs = rp_ + qqc;
                     double dh = 0.0, hh = 0.0;
 #pragma unroll
@@ -278,15 +363,9 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
                             rx = frcp(q.x[c]);
                             double tt = q.z[c] * rx + (q.x[c] > 1.0 ? reg * rx * rx : reg);
                             hc = rd_[c] + q.z[c];
-                            dm = dmax(dm, fabs(rd_[c]));
-                            mus += q.x[c] * q.z[c];
-                            po += SMF(SM::A_C + c, j) * q.x[c];
                             if (BND(j, c)) {
                                 const double rs = frcp(q.s[c]);
                                 tt += q.w[c] * rs;
-                                pm = dmax(pm, fabs(ru_[c]));
-                                mus += q.s[c] * q.w[c];
-                                dob -= SMF(SM::A_U + c, j) * q.w[c];
                                 hc += (-q.w[c] * ru_[c]) * rs - q.w[c];
                             }
                             dc = frcp(tt);
@@ -310,50 +389,7 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
             dl_left = gup1<L>(ddc, gl); ql_left = gup1<L>(qqc, gl);
             if (ACT(0)) { Dd[0] += dl_left; f1[0] += ql_left; }
         }
-        double mu;
-        {
-            const double res = gmax<L>(dmax(pm / nrm_b, dm / nrm_c));
-            mus = gsum<L>(mus); po = gsum<L>(po); dob = gsum<L>(dob);
-            mu = mus / ntot;
-            const double den = dmax(kGapFloor2, fabs(po));
-            const double gap = fabs(po - dob) / den, cgap = ntot * mu / den;
-            if (mode == 0) {
-                int status = -1;
-                if (!(mu == mu) || !(po == po) || mu > 1e100) status = DSP_NUMERICAL;
-                else if (res < Q.feas_tol && gap < Q.tol) status = DSP_OPTIMAL;
-                else if (cgap < Q.tol && res < 10.0 * Q.feas_tol && gap < 10.0 * Q.tol) status = DSP_OPTIMAL;
-                else if (cgap < 1e-3 * Q.tol) status = (res < 100.0 * Q.feas_tol && gap < 1000.0 * Q.tol) ? DSP_OPTIMAL : DSP_NUMERICAL;
-                else if (it == Q.max_iter) status = DSP_MAX_ITER;
-                if (status >= 0) {
-                    if (gl == 0) { Q.obj[p] = po * beta_b * beta_c + kconst; Q.status[p] = status; Q.iters[p] = it + it0; }
-                    if (Q.x_out) {
-                        double *xo_ = Q.x_out + p * (long long)Q.n;
-#pragma unroll
-                        for (int j = 0; j < P; ++j) {
-                            const int t = gl * P + j;
-                            if (t < T) {
-#pragma unroll
-                                for (int c = 0; c < NC; ++c)
-                                    if (HAS(j, c)) {
-                                        const int col = Q.col_idx[t * NC + c];
-                                        xo_[Q.x_perm ? Q.x_perm[col] : col] = pr[j].x[c] * beta_b;
-                                    }
-                            }
-                        }
-                    }
-                    if (Q.y_out) {
-                        double *yo_ = Q.y_out + p * (long long)Q.m;
-#pragma unroll
-                        for (int j = 0; j < P; ++j) {
-                            const int t = gl * P + j;
-                            if (t < T) { const int row = Q.row_idx[t]; yo_[Q.y_perm ? Q.y_perm[row] : row] = pr[j].y * beta_c; }
-                        }
-                    }
-                    if (status != DSP_OPTIMAL && attempt == 0) { mode = 2; attempt = 1; it0 = it + it0; }
-                    else mode = 1;
-                }
-            }
-        }
+        const double mu = mu_keep;
 
         // =========================================================================================== factorisation + predictor solve
         double Wc, Asep, g1, Ainv, Mout = 0.0, Mout2 = 0.0, Cin;
@@ -616,6 +652,7 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
 #undef BND
 #undef ACT
 #undef YN
+#undef NEIGHBOURS
 #undef RESID
 #undef SEP_BACK
 #undef LOCAL_BACK
