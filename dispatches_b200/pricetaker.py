@@ -7,6 +7,7 @@ Same names and argument meaning as the reference functions; the only extension i
   wind_battery_pem_optimize(time_points, input_params, verbose)    wind_battery_PEM_LMP.py:180-298
   record_results(res)                                              wind_battery_LMP.py:272-325
   nuclear_dispatch_optimize(n_time_points, lmps, ...)              nuclear_flowsheet_multiperiod_class.py:72-155
+  pv_battery_hydrogen_optimize(n_time_points, input_params, ...)   solar_battery_hydrogen.py:375-606 (design_opt=False)
 
 Where the reference builds a Pyomo MultiPeriodModel and calls SolverFactory("cbc").solve(m) once per signal,
 these build (and cache) one LPTemplate per (flowsheet, T) and hand the whole batch to the CUDA solver.
@@ -212,6 +213,102 @@ def nuclear_dispatch_optimize(n_time_points, lmps, want_solution=False, **flowsh
     r = sol.solve_host(lmp, None, want_x=want_solution)
     return PriceTakerResult("nuclear", T, lmp, r.obj, r.status, r.iters,
                             sol.to_model_space(r.x) if want_solution else None, sol.t.col_names, {})
+
+
+_SOLAR_COST_KEYS = ("pv_cap_cost", "pv_op_cost", "batt_cap_cost_kw", "batt_cap_cost_kwh", "pem_cap_cost", "pem_op_cost", "pem_var_cost",
+                    "tank_cap_cost_per_kg", "tank_op_cost", "turbine_cap_cost", "turbine_op_cost", "turbine_var_cost", "h2_price_per_kg",
+                    "turbine_min_mw", "turbine_ramp_mw_per_min", "h2_turb_conv")
+
+
+def pv_battery_hydrogen_optimize(n_time_points, input_params, verbose=False, plot=False):
+    """The reference's PV + battery + PEM + hydrogen tank + turbine load-following case (solar_battery_hydrogen.py:375-606) with
+    ``design_opt=False``, batched: ``LMP`` [T] or [N, T], ``load`` / ``pv_resource`` [T] or [N, T].  Same ``input_params`` keys as
+    ``re_h2_parameters`` (solar_battery_hydrogen_inputs.py:79-118).  Returns (design_res, df) like the reference: ``design_res`` with
+    the reference's keys (scalars, or arrays [N] for a batch), ``df`` a dict of the operating series [N, T] under the
+    reference's column names (one pandas frame per scenario is a ``pd.DataFrame({k: v[i] for k, v in df.items()})`` away).
+    design_opt=True is refused: its six size variables couple every period (not banded within the band kernel's limit)."""
+    if input_params.get("design_opt", False):
+        raise NotImplementedError("pv_battery_hydrogen_optimize: design_opt=True is not on the batched GPU path "
+                                  "(six dense size columns); solve the fixed-design LP per candidate size instead")
+    T = int(n_time_points)
+    lmp = np.ascontiguousarray(np.atleast_2d(np.asarray(input_params["LMP"], float))[:, :T])
+    pr = input_params["pv_resource"]
+    if isinstance(pr, dict):       # the reference's {t: {'pv_resource_config': {'capacity_factor': cf}}}
+        cfs = np.array([np.ravel(pr[t]["pv_resource_config"]["capacity_factor"])[0] for t in range(T)], float)
+    else:
+        cfs = np.asarray(pr, float)[..., :T]
+    load = np.asarray(input_params["load"], float)[..., :T]
+    batt_mw = float(input_params.get("batt_mw", 0.0))
+    batt_mwh = float(input_params["batt_mw"] * input_params["batt_hr"]) if "batt_hr" in input_params else float(input_params.get("batt_mwh", 0.0))
+    par = {k: float(input_params[k]) for k in _SOLAR_COST_KEYS if k in input_params}
+    kw = dict(batt_mw=batt_mw, batt_mwh=batt_mwh, pem_mw=float(input_params.get("pem_mw", 0.0)), tank_kg=float(input_params["tank_size"]),
+              turb_mw=float(input_params["turb_mw"]), max_sales=float(input_params.get("max_sales", np.inf)),
+              max_purchases=float(input_params.get("max_purchases", np.inf)))
+    key = ("solar_battery_hydrogen", T, tuple(sorted(kw.items())), tuple(sorted(par.items())),
+           np.asarray(input_params["reserve"], float)[:T].tobytes())
+    if key not in _SOLVERS:
+        _SOLVERS[key] = BatchLPSolver(TP.solar_battery_hydrogen(T, reserve_mw=np.asarray(input_params["reserve"], float)[:T], par=par, **kw))
+    sol = _SOLVERS[key]
+    t = sol.t
+    rp = TP.solar_rparams(T, cfs, input_params["pv_mw"], load)
+    N = max(lmp.shape[0], rp.shape[0])
+    if lmp.shape[0] not in (1, N) or rp.shape[0] not in (1, N):
+        raise ValueError("LMP, load and pv_resource must be one series or one per scenario")
+    lmp = np.ascontiguousarray(np.broadcast_to(lmp, (N, T)))
+    r = sol.solve_host(lmp, rp[0] if rp.shape[0] == 1 else rp, want_x=True)
+    if verbose:
+        print(f"b200ipm: {N} LPs, iterations mean {r.iters.mean():.1f} max {r.iters.max()}, non-optimal {(r.status != OPTIMAL).sum()}")
+    xm = sol.to_model_space(r.x)
+    names = {n: j for j, n in enumerate(t.col_names)}
+
+    def ser(name, blk_level=False):
+        cols = [names.get((f"blk[{k}]." if blk_level else f"blk[{k}].fs.") + name) for k in range(T)]
+        return np.stack([xm[:, c] if c is not None else np.zeros(N) for c in cols], axis=1)
+    P = dict(TP.SOLAR); P.update(par)
+    sz = t.meta["sizes"]
+    k_turb = t.meta["k_turb"]
+    pv_kw = np.broadcast_to(np.asarray(input_params["pv_mw"], float) * 1e3, (N,))
+    pv_gen, grid, pem = ser("pv.electricity[0]"), ser("splitter.grid_elec[0]"), ser("pem.electricity[0]")
+    b_in, b_out, soc = ser("battery.elec_in[0]"), ser("battery.elec_out[0]"), ser("battery.state_of_charge[0]")
+    to_turb, to_pipe, holdup = ser("h2_tank.outlet_to_turbine.flow_mol[0]"), ser("h2_tank.outlet_to_pipeline.flow_mol[0]"), ser("h2_tank.tank_holdup[0]")
+    purchase, sales = ser("grid_purchase", True), ser("grid_sales", True)
+    turb_elec = to_turb * k_turb
+    n_weeks = T / 168.0
+    h2_rev = P["h2_price_per_kg"] / TP.H2_MOLS_PER_KG * to_pipe * P["s_per_ts"]
+    grid_cost = lmp * (purchase - sales) * 1e-3
+    pem_var, turb_var = P["pem_var_cost"] * pem, P["turbine_var_cost"] * turb_elec
+    fixed = pv_kw * P["pv_op_cost"] + sz["pem_kw"] * P["pem_op_cost"] + t.meta["tank_kg"] * P["tank_op_cost"] + sz["turb_kw"] * P["turbine_op_cost"]
+    squeeze = (lambda a: float(a[0])) if N == 1 else (lambda a: a)
+    design_res = {
+        "pv_mw": squeeze(pv_kw * 1e-3), "batt_mw": sz["batt_kw"] * 1e-3, "batt_mwh": sz["batt_kwh"] * 1e-3,
+        "batt_hr": sz["batt_kwh"] / sz["batt_kw"] if sz["batt_kw"] else 0, "pem_mw": sz["pem_kw"] * 1e-3,
+        "tank_tonH2": t.meta["tank_kg"] * P["kg_to_tons"], "turb_mw": sz["turb_kw"] * 1e-3,
+        "capital_cost": t.meta["capital_cost"], "capital_cost_pv": 0.0, "capital_cost_batt_kw": P["batt_cap_cost_kw"] * sz["batt_kw"],
+        "capital_cost_batt_kwh": P["batt_cap_cost_kwh"] * sz["batt_kwh"], "capital_cost_pem": P["pem_cap_cost"] * sz["pem_kw"],
+        "capital_cost_tank": P["tank_cap_cost_per_kg"] * t.meta["tank_kg"], "capital_cost_turb": 0.0,
+        "annual_costs_fixed": squeeze(fixed), "fixed_cost_pv": squeeze(pv_kw * P["pv_op_cost"]), "fixed_cost_pem": sz["pem_kw"] * P["pem_op_cost"],
+        "fixed_cost_tank": t.meta["tank_kg"] * P["tank_op_cost"], "fixed_cost_turb": sz["turb_kw"] * P["turbine_op_cost"],
+        "annual_costs_variable": squeeze((pem_var + turb_var).sum(1)), "variable_cost_batt": 0.0,
+        "variable_cost_pem": squeeze(pem_var.sum(1)), "variable_cost_turb": squeeze(turb_var.sum(1)),
+        "annual_costs_NG": 0.0, "annual_costs_grid": squeeze(grid_cost.sum(1) * 52 / n_weeks),
+        "annual_costs_total": squeeze((grid_cost + pem_var + turb_var).sum(1) * 52 / n_weeks),
+        "annual_rev_h2": squeeze(h2_rev.sum(1) * 52 / n_weeks), "NPV": squeeze(-r.obj * 1e3), "CO2_lb": 0.0,
+        "status": [STATUS_NAMES[int(v)] for v in r.status],
+    }
+    cf2 = np.broadcast_to(np.atleast_2d(cfs), (N, T))
+    df = {
+        "Total PV Generation [MW]": pv_gen * 1e-3, "Total Power Output [MW]": (grid + b_out + turb_elec) * 1e-3,
+        "PV Power Output [MW]": grid * 1e-3, "PV Power to Battery [MW]": b_in * 1e-3,
+        "State of Charge": soc / sz["batt_kwh"] if sz["batt_kwh"] else soc, "Battery Power Output [MW]": b_out * 1e-3,
+        "PV Power to PEM [MW]": pem * 1e-3, "PEM H2 Output [kg]": pem * TP.PEM_ELEC_TO_MOL * P["s_per_ts"] / TP.H2_MOLS_PER_KG,
+        "H2 Sales [kg]": to_pipe * P["s_per_ts"] / TP.H2_MOLS_PER_KG, "Turbine H2 Input [kg]": to_turb * P["s_per_ts"] / TP.H2_MOLS_PER_KG,
+        "Turbine Power [MW]": turb_elec * 1e-3, "Purchased Power [MW]": purchase * 1e-3, "Sold Power [MW]": sales * 1e-3,
+        "Tank Holdup [kg]": holdup / TP.H2_MOLS_PER_KG, "Excess PV [MW]": (pv_kw[:, None] * cf2 - pv_gen) * 1e-3,
+        "Battery Reserve [MW]": ser("battery_reserve", True) * 1e-3, "PEM Reserve [MW]": pem * 1e-3,
+        "Turbine Reserve [MW]": ser("turbine_reserve", True) * 1e-3, "Load [MW]": np.broadcast_to(np.atleast_2d(load), (N, T)),
+        "Grid Income [$]": grid_cost, "H2 Revenue [$]": h2_rev, "Operating Cost [$]": pem_var + turb_var,
+    }
+    return design_res, df
 
 
 def record_results(res: PriceTakerResult, k=0):

@@ -396,6 +396,123 @@ def fossil_surrogate(T: int = 168, par=None) -> LPTemplate:
 
 
 # --------------------------------------------------------------------------------------
+# PV + battery + PEM + hydrogen tank + hydrogen turbine, load following with reserves
+# --------------------------------------------------------------------------------------
+# solar_battery_hydrogen_inputs.py:22-70 (overrides of load_parameters.py; "pem_cap_cost" stays at load_parameters' 1200)
+SOLAR = dict(pv_cap_cost=WIND_CAP_COST, pv_op_cost=WIND_OP_COST, batt_cap_cost_kw=236.36 * 0.5, batt_cap_cost_kwh=254.83 * 0.5,
+             pem_cap_cost=PEM_CAP_COST, pem_op_cost=47.9, pem_var_cost=1.3e-3, tank_cap_cost_per_kg=500.0, tank_op_cost=85.0,
+             turbine_cap_cost=1320.0, turbine_op_cost=11.65, turbine_var_cost=3e-3, h2_price_per_kg=2.5,
+             capacity_requirement=100.0, capacity_credit_battery=0.33, turbine_min_mw=0.0, turbine_ramp_mw_per_min=100.0,
+             h2_turb_conv=0.39 * 33.391, flow_mol_ub=1e5, kg_to_tons=0.00110231, s_per_ts=3600.0)
+
+
+def solar_battery_hydrogen(T: int, batt_mw=0.0, batt_mwh=0.0, pem_mw=0.0, tank_kg=None, turb_mw=100.0, reserve_mw=100.0,
+                           max_sales=1000.0, max_purchases=1000.0, par=None) -> LPTemplate:
+    """pv_battery_hydrogen_optimize with design_opt=False (solar_battery_hydrogen.py:375-457; h2_blend_ratio = 1): PV + battery
+    + PEM + hydrogen tank + hydrogen turbine following a load with a reserve requirement, grid purchases / sales at the LMP.
+    Objective = -NPV*1e-3 (:372).  Sizes are template constants (the reference fixes them, :222-228); the batch runs over
+    cparams = lmp[T] and rparams = [pv_kw*cf_t (T), load_kw_t (T), pv_kw].
+
+    Presolve: arcs substituted (w = z, p = pe, q = i, tank inlet = PEM outlet); nameplate power / energy at their fixed values;
+    energy_throughput dropped (degradation_rate = 0, :173, leaves it in no other row); link equalities substituted, the periodic
+    pairs (:58-61) make state of charge and tank holdup CYCLIC in time; grid_sales - grid_purchase <= max_sales is implied by the
+    bounds (:355-360); the turbine ramp rows (:323-324) are dropped when the ramp limit exceeds the turbine capacity; the
+    capacity requirement (:352) involves constants only and is checked here."""
+    P = dict(SOLAR); P.update(par or {})
+    if tank_kg is None:
+        tank_kg = P["capacity_requirement"] * 1e3 / P["h2_turb_conv"]           # inputs.py:86
+    Bc, Be, Pc, Tc = batt_mw * 1e3, batt_mwh * 1e3, pem_mw * 1e3, turb_mw * 1e3
+    if Bc * P["capacity_credit_battery"] + Tc < P["capacity_requirement"] * 1e3 - 1e-9:
+        raise ValueError("capacity requirement (solar_battery_hydrogen.py:352) cannot be met by the fixed sizes")
+    if not (0.5 * Bc - 1e-9 <= Be <= 8.0 * Bc + 1e-9):
+        raise ValueError("battery duration outside 0.5 .. 8 hours (solar_battery_hydrogen.py:234-235)")
+    reserve = np.broadcast_to(np.asarray(reserve_mw, float), (T,))
+    k_turb = P["s_per_ts"] / H2_MOLS_PER_KG * P["h2_turb_conv"]                  # kW per mol/s sent to the turbine
+    k_res = P["h2_turb_conv"] / H2_MOLS_PER_KG                                  # kW of reserve per mol of holdup
+    ramp = P["turbine_ramp_mw_per_min"] * 1e3
+    iA, iL, iPV = 0, T, 2 * T
+    B = TemplateBuilder(f"solar_battery_hydrogen_T{T}", Pc=T, Pr=2 * T + 1)
+    ann = 52.143 / (T / 168.0)
+    kk = 1e-3 * PA * ann
+    w, g, pe, i, o, s, tt, tp, hd, gp, gs, tr, br = ({} for _ in range(13))
+    have_batt, have_pem = Bc > 0.0, Pc > 0.0
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        w[t] = B.var(p + "pv.electricity[0]", ub=(0.0, {iA + t: 1.0}))                       # solar_pv.py:82-84
+        g[t] = B.var(p + "splitter.grid_elec[0]")
+        if have_pem:
+            pe[t] = B.var(p + "pem.electricity[0]", ub=min(Pc, P["flow_mol_ub"] / PEM_ELEC_TO_MOL))     # pem_max_p :229
+            B.cost(pe[t], kk * P["pem_var_cost"])
+        if have_batt:
+            i[t] = B.var(p + "battery.elec_in[0]", ub=Bc)
+            o[t] = B.var(p + "battery.elec_out[0]", ub=Bc)
+            s[t] = B.var(p + "battery.state_of_charge[0]", ub=Be)
+            br[t] = B.var(f"blk[{t}].battery_reserve", ub=Bc)                                # battery_reserve_lb1
+        tt[t] = B.var(p + "h2_tank.outlet_to_turbine.flow_mol[0]", lb=P["turbine_min_mw"] * 1e3 / k_turb,
+                      ub=min(P["flow_mol_ub"], Tc / k_turb))                                # h2_turbine_pmin :159, turb_max_p :231
+        tp[t] = B.var(p + "h2_tank.outlet_to_pipeline.flow_mol[0]", ub=P["flow_mol_ub"])
+        hd[t] = B.var(p + "h2_tank.tank_holdup[0]", ub=tank_kg * H2_MOLS_PER_KG)             # tank_max_p :230
+        gp[t] = B.var(f"blk[{t}].grid_purchase", ub=max_purchases * 1e3)
+        gs[t] = B.var(f"blk[{t}].grid_sales", ub=max_sales * 1e3)
+        tr[t] = B.var(f"blk[{t}].turbine_reserve")
+        B.cost(gs[t], (0.0, {t: -kk * 1e-3})); B.cost(gp[t], (0.0, {t: kk * 1e-3}))           # grid_cost :361
+        B.cost(tt[t], kk * P["turbine_var_cost"] * k_turb)
+        B.cost(tp[t], -kk * P["h2_price_per_kg"] / H2_MOLS_PER_KG * P["s_per_ts"])           # hydrogen_revenue :354
+    for t in range(T):
+        tm = (t - 1) % T
+        row = {w[t]: 1.0, g[t]: -1.0}                                                       # elec_splitter.py:115-117
+        if have_pem:
+            row[pe[t]] = -1.0
+        if have_batt:
+            row[i[t]] = -1.0
+        B.eq(f"split[{t}]", row)
+        if have_batt:
+            row = {s[t]: 1.0, i[t]: -ETA_C, o[t]: 1.0 / ETA_D}                               # battery.py:145-149, links :44 / :59
+            row[s[tm]] = row.get(s[tm], 0.0) - 1.0
+            B.eq(f"soc[{t}]", row)
+            B.le(f"battery_reserve_lb2[{t}]", {br[t]: 1.0, s[t]: -1.0})
+        row = {hd[t]: 1.0, tp[t]: P["s_per_ts"], tt[t]: P["s_per_ts"]}                        # hydrogen_tank_simplified.py:177-184
+        row[hd[tm]] = row.get(hd[tm], 0.0) - 1.0
+        if have_pem:
+            row[pe[t]] = -P["s_per_ts"] * PEM_ELEC_TO_MOL
+        B.eq(f"tank[{t}]", row)
+        row = {g[t]: 1.0, tt[t]: k_turb, gp[t]: 1.0, gs[t]: -1.0}                             # meet_load :331
+        if have_batt:
+            row[o[t]] = 1.0
+        B.eq(f"meet_load[{t}]", row, (0.0, {iL + t: 1.0}))
+        B.le(f"turbine_reserve_lb1[{t}]", {tr[t]: 1.0, hd[t]: -k_res})
+        B.le(f"turbine_reserve_lb2[{t}]", {tr[t]: 1.0, tt[t]: k_turb}, Tc)
+        r1 = (max(reserve[max(t - 1, 0):t]) if t > 0 else reserve[0]) * 1e3                   # :347-348
+        row = {tr[t]: -1.0, w[t]: 1.0}                                                      # min_reserve :349
+        if have_batt:
+            row[br[t]] = -1.0
+        if have_pem:
+            row[pe[t]] = -1.0
+        B.le(f"min_reserve[{t}]", row, (-r1, {iA + t: 1.0}))
+        if ramp < Tc and T > 1:
+            B.le(f"energy_down_ramp[{t}]", {tt[tm]: k_turb, tt[t]: -k_turb}, ramp)
+            B.le(f"energy_up_ramp[{t}]", {tt[t]: k_turb, tt[tm]: -k_turb}, ramp)
+    cap = (P["batt_cap_cost_kw"] * Bc + P["batt_cap_cost_kwh"] * Be + P["pem_cap_cost"] * Pc + P["tank_cap_cost_per_kg"] * tank_kg)
+    fixed = Pc * P["pem_op_cost"] + tank_kg * P["tank_op_cost"] + Tc * P["turbine_op_cost"]
+    B.obj_const((1e-3 * (cap + PA * fixed), {iPV: 1e-3 * PA * P["pv_op_cost"]}))
+    B.meta.update(kind="solar_battery_hydrogen", T=T, ann=ann, capital_cost=cap, k_turb=k_turb, tank_kg=tank_kg,
+                  sizes=dict(batt_kw=Bc, batt_kwh=Be, pem_kw=Pc, turb_kw=Tc))
+    return B.build(equilibrate=True)         # holdups (1e6 mol) next to powers (1e5 kW) and flows (1e2 mol/s)
+
+
+def solar_rparams(T, pv_cfs, pv_mw, load_mw):
+    """rparams rows of solar_battery_hydrogen: [pv_kw*cf_t (T), load_kw_t (T), pv_kw]; pv_cfs / load_mw [T] or [N, T], pv_mw scalar or [N]"""
+    cf = np.atleast_2d(np.asarray(pv_cfs, float)); ld = np.atleast_2d(np.asarray(load_mw, float))
+    pv = np.atleast_1d(np.asarray(pv_mw, float)) * 1e3
+    N = max(cf.shape[0], ld.shape[0], pv.size)
+    out = np.empty((N, 2 * T + 1))
+    out[:, :T] = pv[:, None] * cf
+    out[:, T:2 * T] = ld * 1e3
+    out[:, 2 * T] = pv
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # double-loop operation model: tracking / bidding LPs (SURVEY.md §8(f)-2)
 # --------------------------------------------------------------------------------------
 BATT_REP_COST_KWH = BATT_CAP_COST_KW * 0.5 / 4.0     # load_parameters.py:48

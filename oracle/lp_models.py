@@ -470,3 +470,171 @@ def nuclear_report_raw(lmp, h2_price, pem_cap_mw, pem_capex=400.0, tank_cap=0.0,
     B.lb[v["Hp", 0]] = B.ub[v["Hp", 0]] = 0.0
     B.c0 = -(dep + k * (-fom - dep) - capex / cf)
     return B.finish(dict(kind="nuclear_report", T=T, v=v, capex=capex, fom=fom))
+
+
+# --------------------------------------------------------------------------------------
+# A.6  PV + battery + PEM + hydrogen tank + hydrogen turbine, load following with reserves
+# --------------------------------------------------------------------------------------
+# constants of case_studies/renewables_case/solar_battery_hydrogen_inputs.py:22-70 (they override load_parameters.py where the
+# names coincide; "pem_cap_cost" keeps load_parameters' 1200 because the inputs file defines pem_cap_cost_kw instead)
+SOLAR = dict(
+    h2_blend_ratio=1.0, s_per_ts=3600.0, timestep_hrs=1.0,
+    pv_cap_cost=WIND_CAP_COST, pv_op_cost=WIND_OP_COST,            # inputs.py:96-97 reuse the wind numbers
+    batt_cap_cost_kw=236.36 * 0.5, batt_cap_cost_kwh=254.83 * 0.5,  # tax incentive 0.5
+    pem_cap_cost=PEM_CAP_COST, pem_op_cost=47.9, pem_var_cost=1.3 / 1000.0,
+    tank_cap_cost_per_kg=500.0, tank_op_cost=0.17 * 500.0,
+    turbine_cap_cost=1320.0, turbine_op_cost=11.65, turbine_var_cost=3.0 / 1000.0,
+    h2_price_per_kg=2.5, capacity_requirement=100.0, capacity_credit_battery=0.33,
+    turbine_min_mw=0.0, turbine_ramp_mw_per_min=100.0,
+    h2_turb_conv=0.39 * 33.391, ng_turb_conv=0.33 * 13.09, mmbtu_to_ng_kg=20.133,
+    pv_mw=200.0, batt_mw=0.0, batt_mwh=0.0, pem_mw=0.0, turb_mw=100.0,
+    flow_mol_ub=1e5,                                                 # properties/h2_ideal_vap.py:86 state bound
+    kg_to_tons=0.00110231,
+)
+SOLAR["tank_size"] = SOLAR["capacity_requirement"] * 1e3 / SOLAR["h2_turb_conv"]       # inputs.py:86 (blend ratio 1)
+
+
+def solar_default_series():
+    """inputs.py:57-61: sinusoidal PV capacity factors, 100 MW load and reserve, 3 $/MMBtu gas, for one 24-hour day"""
+    return dict(pv_cfs=np.sin(np.deg2rad(np.linspace(0, 180, 24))), load_mw=np.full(24, 100.0), reserve_mw=np.full(24, 100.0),
+                ng_prices=np.full(24, 3.0))
+
+
+def solar_battery_hydrogen_raw(lmp, design_opt, par=None, pv_cfs=None, load_mw=None, reserve_mw=None, max_sales=1000.0, max_purchases=1000.0):
+    """Raw LP of pv_battery_hydrogen_optimize (case_studies/renewables_case/solar_battery_hydrogen.py:375-457): per-period flowsheet
+    :123-174 (create_model with re_type='pv', RE_flowsheet.py:338-396; unit_models/solar_pv.py:82-84,
+    hydrogen_tank_simplified.py:177-184), linking / periodic pairs :33-61, size_constraints :205-236, capital / fixed / variable
+    costs :238-305, add_load_following_obj :308-372.  h2_blend_ratio = 1: no natural gas (ng_kg is a zero Param, :149-150).
+    Objective = -NPV * 1e-3 (:372).  Pinned to the reference's known answers tests/test_solar_battery_hydrogen.py:20-48."""
+    P = dict(SOLAR); P.update(par or {})
+    d = solar_default_series()
+    cf = np.asarray(d["pv_cfs"] if pv_cfs is None else pv_cfs, float)
+    load = np.asarray(d["load_mw"] if load_mw is None else load_mw, float)
+    reserve = np.asarray(d["reserve_mw"] if reserve_mw is None else reserve_mw, float)
+    lmp = np.asarray(lmp, float)
+    T = lmp.size
+    assert cf.size == T and load.size == T and reserve.size == T
+    B = _Builder()
+    v = {}
+    batt_mwh = P["batt_mwh"] if "batt_hr" not in P else P["batt_mw"] * P["batt_hr"]
+    fmax = P["flow_mol_ub"]
+    k_turb = P["s_per_ts"] / H2_MOLS_PER_KG * P["h2_turb_conv"]              # kW of turbine output per mol/s of hydrogen (:147,:157)
+    for t in range(T):
+        p = f"blk[{t}].fs."
+        fx = (lambda val: None) if design_opt else (lambda val: val)
+        v["C", t] = B.var(p + "pv.system_capacity", fix=fx(P["pv_mw"] * 1e3))              # :166-170
+        v["w", t] = B.var(p + "pv.electricity[0]")
+        v["z", t] = B.var(p + "splitter.electricity[0]")
+        v["g", t] = B.var(p + "splitter.grid_elec[0]")
+        v["p", t] = B.var(p + "splitter.pem_elec[0]")
+        v["q", t] = B.var(p + "splitter.battery_elec[0]")
+        v["P", t] = B.var(p + "battery.nameplate_power", ub=1e8, fix=fx(P["batt_mw"] * 1e3))
+        v["E", t] = B.var(p + "battery.nameplate_energy", ub=1e9, fix=fx(batt_mwh * 1e3))
+        v["s0", t] = B.var(p + "battery.initial_state_of_charge")
+        v["e0", t] = B.var(p + "battery.initial_energy_throughput")
+        v["i", t] = B.var(p + "battery.elec_in[0]")
+        v["o", t] = B.var(p + "battery.elec_out[0]")
+        v["s", t] = B.var(p + "battery.state_of_charge[0]")
+        v["e", t] = B.var(p + "battery.energy_throughput[0]")
+        v["pe", t] = B.var(p + "pem.electricity[0]", lb=-INF)
+        v["h", t] = B.var(p + "pem.outlet.flow_mol[0]", ub=fmax)
+        v["ti", t] = B.var(p + "h2_tank.inlet.flow_mol[0]", ub=fmax)
+        v["tt", t] = B.var(p + "h2_tank.outlet_to_turbine.flow_mol[0]", ub=fmax)
+        v["tp", t] = B.var(p + "h2_tank.outlet_to_pipeline.flow_mol[0]", ub=fmax)
+        v["hp", t] = B.var(p + "h2_tank.tank_holdup_previous[0]")
+        v["hd", t] = B.var(p + "h2_tank.tank_holdup[0]")
+        v["gp", t] = B.var(f"blk[{t}].grid_purchase", ub=max_purchases * 1e3)               # :358-360
+        v["gs", t] = B.var(f"blk[{t}].grid_sales", ub=max_sales * 1e3)                      # :355-357
+        v["tr", t] = B.var(f"blk[{t}].turbine_reserve")
+        v["br", t] = B.var(f"blk[{t}].battery_reserve")
+        B.le({v["w", t]: 1.0, v["C", t]: -cf[t]})                                           # solar_pv.py:82-84
+        B.eq({v["w", t]: 1.0, v["z", t]: -1.0})                                             # arc pv_to_splitter
+        B.eq({v["z", t]: 1.0, v["g", t]: -1.0, v["p", t]: -1.0, v["q", t]: -1.0})           # elec_splitter.py:115-117
+        B.eq({v["p", t]: 1.0, v["pe", t]: -1.0})                                            # arc splitter_to_pem
+        B.eq({v["q", t]: 1.0, v["i", t]: -1.0})                                             # arc splitter_to_battery
+        B.eq({v["h", t]: 1.0, v["pe", t]: -PEM_ELEC_TO_MOL})                                # pem_electrolyzer.py:111-114
+        B.eq({v["ti", t]: 1.0, v["h", t]: -1.0})                                            # arc pem_to_tank
+        B.eq({v["hd", t]: 1.0, v["hp", t]: -1.0, v["ti", t]: -P["s_per_ts"], v["tp", t]: P["s_per_ts"], v["tt", t]: P["s_per_ts"]})
+        B.eq({v["s", t]: 1.0, v["s0", t]: -1.0, v["i", t]: -ETA_C, v["o", t]: 1.0 / ETA_D})  # battery.py:145-149
+        B.eq({v["e", t]: 1.0, v["e0", t]: -1.0, v["i", t]: -0.5, v["o", t]: -0.5})           # battery.py:151-153
+        B.le({v["s", t]: 1.0, v["E", t]: -1.0})                                              # battery.py:155-157, degradation_rate = 0 (:173)
+        B.le({v["i", t]: 1.0, v["P", t]: -1.0})
+        B.le({v["o", t]: 1.0, v["P", t]: -1.0})
+        B.le({v["tt", t]: -k_turb}, -P["turbine_min_mw"] * 1e3)                              # h2_turbine_pmin :159
+    for t in range(T - 1):                                                                   # :42-47
+        B.eq({v["hd", t]: 1.0, v["hp", t + 1]: -1.0})
+        B.eq({v["s", t]: 1.0, v["s0", t + 1]: -1.0})
+        B.eq({v["e", t]: 1.0, v["e0", t + 1]: -1.0})
+        B.eq({v["P", t]: 1.0, v["P", t + 1]: -1.0})
+    B.eq({v["hd", T - 1]: 1.0, v["hp", 0]: -1.0})                                            # :58-61
+    B.eq({v["s", T - 1]: 1.0, v["s0", 0]: -1.0})
+    if T > 1:
+        B.eq({v["P", T - 1]: 1.0, v["P", 0]: -1.0})
+    # ---- size_constraints :205-236
+    fx = (lambda val: None) if design_opt else (lambda val: val)
+    pv_base = P["pv_mw"] * 1e3
+    Va = B.var("pv_add_system_capacity", ub=1e7, fix=fx(0.0))
+    Bc = B.var("battery_system_capacity", ub=1e7, fix=fx(P["batt_mw"] * 1e3))
+    Be = B.var("battery_system_energy", fix=fx(batt_mwh * 1e3))
+    Pc = B.var("pem_system_capacity", ub=1e7, fix=fx(P["pem_mw"] * 1e3))
+    Ts = B.var("h2_tank_size", ub=1e7, fix=fx(P["tank_size"]))
+    Tc = B.var("turb_system_capacity", lb=P["turb_mw"] * 1e3, ub=1e8, fix=fx(P["turb_mw"] * 1e3))
+    for t in range(T):
+        B.le({v["C", t]: 1.0, Va: -1.0}, pv_base)
+        B.le({v["P", t]: 1.0, Bc: -1.0})
+        B.le({v["E", t]: 1.0, Be: -1.0})
+        B.le({v["pe", t]: 1.0, Pc: -1.0})
+        B.le({v["hd", t]: 1.0 / H2_MOLS_PER_KG, Ts: -1.0})
+        B.le({v["tt", t]: k_turb, Tc: -1.0})
+    B.le({Bc: 0.5, Be: -1.0})                                                                # battery between 0.5 and 8 hours
+    B.le({Be: 1.0, Bc: -8.0})
+    # ---- add_load_following_obj :308-372
+    ramp = P["turbine_ramp_mw_per_min"] * 1e3
+    for t in range(T):
+        tprev = (t - 1) % T
+        if T > 1:
+            B.le({v["tt", tprev]: k_turb, v["tt", t]: -k_turb}, ramp)                        # :323-324
+            B.le({v["tt", t]: k_turb, v["tt", tprev]: -k_turb}, ramp)
+        B.eq({v["g", t]: 1.0, v["o", t]: 1.0, v["tt", t]: k_turb, v["gp", t]: 1.0, v["gs", t]: -1.0}, load[t] * 1e3)    # meet_load :328-331
+        B.le({v["tr", t]: 1.0, v["hd", t]: -P["h2_turb_conv"] / H2_MOLS_PER_KG})            # turbine_reserve_lb1 (blend ratio 1: no gas reserve)
+        B.le({v["tr", t]: 1.0, Tc: -1.0, v["tt", t]: k_turb})                                # turbine_reserve_lb2
+        B.le({v["br", t]: 1.0, Bc: -1.0})
+        B.le({v["br", t]: 1.0, v["s", t]: -1.0})
+        r1 = (max(reserve[max(t - int(1 / P["timestep_hrs"]), 0):t]) if t > 0 else reserve[0]) * 1e3                  # :347-348
+        # total_reserve = battery_reserve + turbine_reserve + (C cf - w) + pem.electricity >= reserve_over_1hr
+        B.le({v["br", t]: -1.0, v["tr", t]: -1.0, v["C", t]: -cf[t], v["w", t]: 1.0, v["pe", t]: -1.0}, -r1)
+        B.le({Bc: -P["capacity_credit_battery"], Tc: -1.0}, -P["capacity_requirement"] * 1e3)                         # cap_requirement :352
+        B.le({v["gs", t]: 1.0, v["gp", t]: -1.0}, max_sales * 1e3)                            # :356
+        B.le({v["gp", t]: 1.0, v["gs", t]: -1.0}, max_purchases * 1e3)                        # :359
+    n_weeks = T / 168.0
+    ann = 52.143 / n_weeks
+    npv = {}
+    cap_const = P["turbine_cap_cost"] * P["turb_mw"] * 1e3            # - turb_cap_cost * (Tc - turb_mw*1e3): the constant part
+    _add(npv, Va, -P["pv_cap_cost"]); _add(npv, Bc, -P["batt_cap_cost_kw"]); _add(npv, Be, -P["batt_cap_cost_kwh"])
+    _add(npv, Pc, -P["pem_cap_cost"]); _add(npv, Ts, -P["tank_cap_cost_per_kg"]); _add(npv, Tc, -P["turbine_cap_cost"])
+    _add(npv, Va, -PA * P["pv_op_cost"]); _add(npv, Pc, -PA * P["pem_op_cost"]); _add(npv, Ts, -PA * P["tank_op_cost"])
+    _add(npv, Tc, -PA * P["turbine_op_cost"])
+    fixed_const = -PA * pv_base * P["pv_op_cost"]
+    for t in range(T):
+        B.cost_lmp(v["gs", t], t, -1e-3 * PA * ann * 1e-3, lmp)                               # grid_cost = LMP (purchase - sales) 1e-3
+        B.cost_lmp(v["gp", t], t, +1e-3 * PA * ann * 1e-3, lmp)
+        _add(npv, v["pe", t], -PA * ann * P["pem_var_cost"])
+        _add(npv, v["tt", t], -PA * ann * P["turbine_var_cost"] * k_turb)
+        _add(npv, v["tp", t], PA * ann * P["h2_price_per_kg"] / H2_MOLS_PER_KG * P["s_per_ts"])
+    for j, val in npv.items():
+        B.cost(j, -val * 1e-3)
+    B.c0 = -(cap_const + fixed_const) * 1e-3
+    meta = dict(kind="solar_battery_hydrogen", T=T, v=v, Va=Va, Bc=Bc, Be=Be, Pc=Pc, Ts=Ts, Tc=Tc, ann=ann, par=P, k_turb=k_turb,
+                pv_base=pv_base, design_opt=bool(design_opt))
+    return B.finish(meta)
+
+
+def solar_report(lp: RawLP, x):
+    """the entries of design_res the reference's test asserts (solar_battery_hydrogen.py:513-548)"""
+    m, P = lp.meta, lp.meta["par"]
+    cap = (P["pv_cap_cost"] * x[m["Va"]] + P["batt_cap_cost_kw"] * x[m["Bc"]] + P["batt_cap_cost_kwh"] * x[m["Be"]]
+           + P["pem_cap_cost"] * x[m["Pc"]] + P["tank_cap_cost_per_kg"] * x[m["Ts"]]
+           + P["turbine_cap_cost"] * (x[m["Tc"]] - P["turb_mw"] * 1e3))
+    return dict(pv_mw=(m["pv_base"] + x[m["Va"]]) * 1e-3, batt_mw=x[m["Bc"]] * 1e-3, batt_mwh=x[m["Be"]] * 1e-3, pem_mw=x[m["Pc"]] * 1e-3,
+                tank_tonH2=x[m["Ts"]] * P["kg_to_tons"], turb_mw=x[m["Tc"]] * 1e-3, capital_cost=cap,
+                NPV=-(lp.c @ x + lp.c0) * 1e3)

@@ -20,6 +20,10 @@ Writes
                            :168-175 self-schedule bids, :245-252 thermal-generator bid prices): the first 48 h of
                            309_WIND_1-RTCF / 309_DALMP / 309_RTLMP and the asserted vectors (read with ``ast``); the wind + PEM
                            tracker's known answers (tests/test_wind_PEM_double_loop.py:55-121).
+  solar_golden.json     -- known answers of the reference's PV + battery + hydrogen price-taker test
+                           (case_studies/renewables_case/tests/test_solar_battery_hydrogen.py:20-48: capital cost, NPV, optimal sizes,
+                           every ``pytest.approx`` with its tolerance, read with ``ast``) and the 24 prices the case runs on
+                           (load_parameters.py:62-88: 303 DA LMPs after the reference's date filter, first day).
 No reference SOURCE is copied: only numeric data and test constants.
 """
 import ast
@@ -70,8 +74,41 @@ def double_loop():
     json.dump(gold, open(OUT / "double_loop_golden.json", "w"))
 
 
+def solar():
+    rc = REF / "case_studies" / "renewables_case"
+    tree = ast.parse(open(rc / "tests" / "test_solar_battery_hydrogen.py").read())
+    gold = {}
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        checks = {}
+        for node in ast.walk(fn):
+            # assert des_res['key'] == pytest.approx(value, rel=.. | abs=..)
+            if isinstance(node, ast.Assert) and isinstance(node.test, ast.Compare) and isinstance(node.test.left, ast.Subscript):
+                key = ast.literal_eval(node.test.left.slice)
+                call = node.test.comparators[0]
+                val = float(ast.literal_eval(call.args[0]))
+                tol = {k.arg: float(ast.literal_eval(k.value)) for k in call.keywords}
+                checks[key] = dict(value=val, **tol)
+        overrides = {}
+        for node in ast.walk(fn):
+            if isinstance(node, ast.Assign) and isinstance(node.targets[0], ast.Subscript) and isinstance(node.targets[0].value, ast.Name) \
+                    and node.targets[0].value.id == "params":
+                overrides[ast.literal_eval(node.targets[0].slice)] = ast.literal_eval(node.value)
+        gold[fn.name] = dict(params=overrides, expect=checks)
+    # the price series of the case: load_parameters.py:62-88 (date filter, bus 303, DA market), first 24 hours
+    df = pd.read_csv(rc / "data" / "Wind_Thermal_Dispatch.csv")
+    df.index = pd.to_datetime(df["DateTime"])
+    start = pd.Timestamp("2020-01-02 00:00:00")
+    ix = pd.date_range(start=start, end=start + pd.offsets.DateOffset(days=365) - pd.offsets.DateOffset(hours=1), freq="1h")
+    ix = ix[(ix.day != 29) | (ix.month != 2)]
+    df = df[df.index.isin(ix)]
+    gold["lmp_24"] = [float(v) for v in df["303_DALMP"].values[:24]]
+    json.dump(gold, open(OUT / "solar_golden.json", "w"), indent=1)
+    return gold
+
+
 def main():
     double_loop()
+    solar()
     rc = REF / "case_studies" / "renewables_case"
     df = pd.read_csv(rc / "data" / "Wind_Thermal_Dispatch.csv")
     assert len(df) == 8736
@@ -119,4 +156,9 @@ def main():
 
 if __name__ == "__main__":
     import sys
-    double_loop() if sys.argv[1:] == ["double_loop"] else main()
+    if sys.argv[1:] == ["double_loop"]:
+        double_loop()
+    elif sys.argv[1:] == ["solar"]:
+        print(solar())
+    else:
+        main()

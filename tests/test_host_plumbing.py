@@ -50,6 +50,11 @@ def test_pricetaker_api_plumbing(stand_in, tmp_path):
     G.test_sweep_drivers_write_reference_shaped_results(tmp_path)
 
 
+def test_solar_api_plumbing(stand_in):
+    import test_solar_battery_hydrogen as SB
+    SB.check_reference_shaped_api()
+
+
 def test_double_loop_api_plumbing(stand_in):
     import test_double_loop as D
     D._check_tracker(None)

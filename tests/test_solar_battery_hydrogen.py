@@ -1,0 +1,154 @@
+"""PV + battery + PEM + hydrogen tank + turbine price-taker (solar_battery_hydrogen.py:375-457): the oracle restatement against the
+reference's known answers (tests/test_solar_battery_hydrogen.py:20-48 -> tests/golden/solar_golden.json), the product template
+against the oracle, and the CUDA path against both."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+from scipy.optimize import linprog
+
+from dispatches_b200 import scenarios as SC, templates as TP
+from oracle import highs as H, lp_models as L
+
+GOLD = json.load(open(Path(__file__).parent / "golden" / "solar_golden.json"))
+LMP = np.array(GOLD["lmp_24"])
+
+
+def check(rep, expect):
+    for k, e in expect.items():
+        assert rep[k] == pytest.approx(e["value"], rel=e.get("rel"), abs=e.get("abs")), k
+
+
+def solve_template(t, cp, rp):
+    c, b, u, k = t.instantiate(cp, rp)
+    r = linprog(c, A_eq=t.A, b_eq=b, bounds=[(0, None if not np.isfinite(v) else v) for v in u], method="highs-ds")
+    assert r.status == 0, r.message
+    return r.fun + k, r.x
+
+
+def test_oracle_reproduces_the_reference_known_answers():
+    """both reference tests, every asserted entry with the reference's own tolerance -- and the NPVs to 1e-8, far inside it
+    (the fixed design has no battery; the optimised design has a 303 MW / 151 MWh battery that cycles: the only committed
+    price-taker answer with active storage)"""
+    g = GOLD["test_solar_batt_hydrogen_fixed_design"]
+    lp = L.solar_battery_hydrogen_raw(LMP, False)
+    obj, x = H.solve(lp)[:2]
+    rep = L.solar_report(lp, x)
+    check(rep, g["expect"])
+    assert rep["NPV"] == pytest.approx(g["expect"]["NPV"]["value"], rel=1e-8)
+    g = GOLD["test_solar_batt_hydrogen_optimize"]
+    lp = L.solar_battery_hydrogen_raw(LMP, True, dict(pv_mw=float(g["params"]["pv_mw"]), turb_mw=float(g["params"]["turb_mw"])))
+    obj, x = H.solve(lp)[:2]
+    rep = L.solar_report(lp, x)
+    check(rep, g["expect"])
+    assert rep["NPV"] == pytest.approx(g["expect"]["NPV"]["value"], rel=1e-8)
+    assert rep["capital_cost"] == pytest.approx(g["expect"]["capital_cost"]["value"], rel=1e-7)
+    v = lp.meta["v"]
+    assert max(x[v["o", t]] for t in range(24)) > 4e4          # the battery (sized by the capacity requirement: 0.33 x 303 MW) discharges up to 49 MW
+
+
+CASES = [dict(), dict(batt_mw=50.0, batt_mwh=200.0), dict(batt_mw=50.0, batt_mwh=200.0, pem_mw=20.0),
+         dict(pem_mw=40.0, turb_mw=120.0, par=dict(turbine_ramp_mw_per_min=0.03), reserve_mw=60.0)]
+
+
+@pytest.mark.parametrize("kw", CASES)
+def test_template_matches_the_raw_oracle(kw):
+    d = L.solar_default_series()
+    kw = dict(kw)
+    t = TP.solar_battery_hydrogen(24, **kw)
+    assert t.w <= 32
+    par = dict(kw.pop("par", {}))
+    reserve = np.full(24, kw.pop("reserve_mw", 100.0))
+    par.update(kw)
+    rng = np.random.default_rng(5)
+    for k in range(3):
+        lmp = LMP * rng.lognormal(0, 0.3, 24) if k else LMP
+        load = d["load_mw"] * (rng.uniform(0.7, 1.2, 24) if k else 1.0)
+        cfs = d["pv_cfs"] * (rng.uniform(0.5, 1.0, 24) if k else 1.0)
+        rp = TP.solar_rparams(24, cfs, 200.0, load)[0]
+        a, _ = solve_template(t, lmp, rp)
+        b = H.solve(L.solar_battery_hydrogen_raw(lmp, False, par, pv_cfs=cfs, load_mw=load, reserve_mw=reserve))[0]
+        assert a == pytest.approx(b, rel=1e-10, abs=1e-8)
+
+
+def test_template_known_answer_and_refusals():
+    d = L.solar_default_series()
+    t = TP.solar_battery_hydrogen(24)
+    a, _ = solve_template(t, LMP, TP.solar_rparams(24, d["pv_cfs"], 200.0, d["load_mw"])[0])
+    g = GOLD["test_solar_batt_hydrogen_fixed_design"]["expect"]
+    assert -a * 1e3 == pytest.approx(g["NPV"]["value"], rel=1e-8)
+    assert t.meta["capital_cost"] == pytest.approx(g["capital_cost"]["value"], abs=g["capital_cost"]["abs"])
+    assert t.meta["tank_kg"] * TP.SOLAR["kg_to_tons"] == pytest.approx(g["tank_tonH2"]["value"], rel=g["tank_tonH2"]["rel"])
+    with pytest.raises(ValueError):
+        TP.solar_battery_hydrogen(24, turb_mw=50.0)              # capacity requirement
+    with pytest.raises(ValueError):
+        TP.solar_battery_hydrogen(24, batt_mw=10.0, batt_mwh=200.0)      # 20-hour battery
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", CASES[:3])
+def test_gpu_solar_battery_hydrogen_parity(kw):
+    """the CUDA path (band kernel, cyclic template) on a batch of price / load / PV scenarios vs the raw oracle LP; scenario 0 of the
+    default sizes is the reference's own case: its known NPV comes out of the GPU"""
+    import torch
+    from dispatches_b200.solver import BatchLPSolver
+    d = L.solar_default_series()
+    t = TP.solar_battery_hydrogen(24, **kw)
+    sol = BatchLPSolver(t)
+    rng = np.random.default_rng(17)
+    N = 256
+    lmp = np.vstack([LMP[None], SC.c2(N - 1)[0] * 0.5])
+    load = np.vstack([d["load_mw"][None], d["load_mw"][None] * rng.uniform(0.7, 1.2, (N - 1, 24))])
+    cfs = np.vstack([d["pv_cfs"][None], d["pv_cfs"][None] * rng.uniform(0.5, 1.0, (N - 1, 24))])
+    rp = TP.solar_rparams(24, cfs, 200.0, load)
+    out = sol.solve(torch.tensor(lmp, device="cuda"), torch.tensor(rp, device="cuda"))
+    assert int((out.status != 0).sum()) == 0
+    obj = out.obj.cpu().numpy()
+    idx = [0] + list(rng.choice(N, 24, replace=False))
+    ref = np.array([H.solve(L.solar_battery_hydrogen_raw(lmp[k], False, dict(kw), pv_cfs=cfs[k], load_mw=load[k]))[0] for k in idx])
+    assert (np.abs(obj[idx] - ref) / np.maximum(1.0, np.abs(ref))).max() < 1e-6
+    if not kw:
+        assert -obj[0] * 1e3 == pytest.approx(GOLD["test_solar_batt_hydrogen_fixed_design"]["expect"]["NPV"]["value"], rel=1e-6)
+
+
+def _reference_params():
+    """re_h2_parameters as the reference's test uses it (solar_battery_hydrogen_inputs.py:79-118, test :21-24)"""
+    d = L.solar_default_series()
+    S = TP.SOLAR
+    return dict(pv_mw=200, batt_mw=0, batt_mwh=0, pem_mw=0, tank_size=S["capacity_requirement"] * 1e3 / S["h2_turb_conv"], turb_mw=100,
+                pv_resource={t: {"pv_resource_config": {"capacity_factor": d["pv_cfs"][t]}} for t in range(24)},
+                load=d["load_mw"], reserve=d["reserve_mw"], LMP=LMP, NG_prices=d["ng_prices"], max_sales=1000, max_purchases=1000,
+                design_opt=False, h2_price_per_kg=2.5)
+
+
+def check_reference_shaped_api():
+    """pv_battery_hydrogen_optimize with the reference's input dict: the asserted entries of design_res, then a batch"""
+    from dispatches_b200 import pricetaker as PT
+    params = _reference_params()
+    des, df = PT.pv_battery_hydrogen_optimize(24, params)
+    g = GOLD["test_solar_batt_hydrogen_fixed_design"]["expect"]
+    assert des["tank_tonH2"] == pytest.approx(g["tank_tonH2"]["value"], rel=g["tank_tonH2"]["rel"])
+    assert des["capital_cost"] == pytest.approx(g["capital_cost"]["value"], abs=g["capital_cost"]["abs"])
+    assert des["NPV"] == pytest.approx(g["NPV"]["value"], rel=1e-6)
+    assert des["status"] == ["optimal"]
+    # the load is met every hour: PV to grid + turbine + purchases - sales (no battery, no PEM)
+    out = df["Total Power Output [MW]"] + df["Purchased Power [MW]"] - df["Sold Power [MW]"]
+    assert np.abs(out - df["Load [MW]"]).max() < 1e-3
+    # NPV recomposed from the reported parts (solar_battery_hydrogen.py:368-371)
+    npv = -des["capital_cost"] + TP.PA * ((-des["annual_costs_total"] + des["annual_rev_h2"]) * 52.143 / 52 - des["annual_costs_fixed"])
+    assert npv == pytest.approx(des["NPV"], rel=1e-6)
+    # a batch: three price scenarios, battery + PEM present, against the oracle
+    params.update(batt_mw=50, batt_hr=4, pem_mw=20, LMP=np.stack([LMP, 1.5 * LMP, LMP[::-1]]))
+    des, df = PT.pv_battery_hydrogen_optimize(24, params)
+    ref = [-H.solve(L.solar_battery_hydrogen_raw(l, False, dict(batt_mw=50.0, batt_mwh=200.0, pem_mw=20.0)))[0] * 1e3 for l in params["LMP"]]
+    assert np.allclose(des["NPV"], ref, rtol=1e-6)
+    assert df["State of Charge"].shape == (3, 24) and df["State of Charge"].max() <= 1.0 + 1e-6
+    params["design_opt"] = True
+    with pytest.raises(NotImplementedError):
+        PT.pv_battery_hydrogen_optimize(24, params)
+
+
+@pytest.mark.gpu
+def test_gpu_reference_shaped_api():
+    check_reference_shaped_api()
