@@ -28,6 +28,8 @@
 #include <string>
 #include <vector>
 
+#include "dsp_band.cuh"
+
 #define DSP_VERSION "dsp_lp 0.2 (sm_100a band-IPM + stage kernels)"
 
 namespace {
@@ -147,65 +149,11 @@ __device__ __forceinline__ Hot hot_views(const unsigned char *base, const KParam
     return h;
 }
 
-__device__ __forceinline__ double dmaxd(double a, double b) { return a > b ? a : b; }
-__device__ __forceinline__ double frcpd(double x) {          // reciprocal: MUFU seed + 2 Newton steps (no IEEE division)
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-
-// ---- band LDL' of M.  Lower band, row-major, W1 = W+1 slots per row: Mb[i*W1+k] = M[i][i-k]; the array carries W
-// ---- zero rows in front and behind (no bounds checks in the sweeps).  On exit the diagonal slot holds 1/d_i (0 for a
-// ---- non-positive pivot) and the off-diagonal slots the UNSCALED column entries L[i][i-k]*d_{i-k}.  One warp.
-template <int W>
-__device__ __forceinline__ void band_factor(double *Mb, int m, int lane) {
-    constexpr int W1 = W + 1, NP = W * W, PASSES = (NP + 31) / 32;
-    int off_lr[PASSES], off_lq[PASSES], off_t[PASSES];
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) {
-        const int idx = lane + 32 * ps;
-        const int r = 1 + idx / W, q = 1 + idx % W;
-        const bool ok = (idx < NP) && (q <= r);
-        off_lr[ps] = ok ? r * W1 + r : -1;
-        off_lq[ps] = q * W1 + q;
-        off_t[ps] = r * W1 + (r - q);
-    }
-    for (int j = 0; j < m; ++j) {
-        double *row = Mb + j * W1;
-        const double piv = row[0];
-        const double inv = piv > 0.0 ? frcpd(piv) : 0.0;
-#pragma unroll
-        for (int ps = 0; ps < PASSES; ++ps) {
-            if (off_lr[ps] >= 0) row[off_t[ps]] -= row[off_lr[ps]] * row[off_lq[ps]] * inv;
-        }
-        __syncwarp();
-        if (lane == 0) row[0] = inv;
-    }
-    __syncwarp();
-}
-
-// ---- solve M v = r in place (v carries W padding entries in front and behind).  One warp.
-template <int W>
-__device__ __forceinline__ void band_solve(const double *Mb, double *v, int m, int lane) {
-    constexpr int W1 = W + 1;
-    const int r = (lane % W) + 1;                 // lanes >= W idle in the sweeps (W <= 16 < 32)
-    const bool on = lane < W;                     // W <= 32
-    for (int j = 0; j < m; ++j) {                 // forward: L t = r  (column sweeps)
-        const double t = v[j] * Mb[j * W1];
-        if (on) v[j + r] -= Mb[(j + r) * W1 + r] * t;
-        __syncwarp();
-    }
-    for (int j = lane; j < m; j += 32) v[j] *= Mb[j * W1];      // t' = D^-1 t
-    __syncwarp();
-    for (int i = m - 1; i > 0; --i) {             // backward: L' v = t'
-        const double vi = v[i];
-        if (on) v[i - r] -= Mb[(i - r) * W1] * Mb[i * W1 + r] * vi;
-        __syncwarp();
-    }
-}
+// band LDL' / substitution sweeps (dsp_band.cuh)
+using band::dmaxd;
+using band::frcpd;
+using band::band_factor;
+using band::band_solve;
 
 struct Work {   // per-warp shared-memory vectors
     double *x, *z, *c, *rd, *d, *dx, *cor, *rx;     // n
