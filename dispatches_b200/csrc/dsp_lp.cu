@@ -1079,6 +1079,7 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         const stagewb::StageParams &S = T->sp;
         Q.T = S.T; Q.a = S.a; Q.binv = S.binv; Q.hf = S.hf; Q.dl = S.dl; Q.dur = S.dur; Q.krev = S.krev;
         Q.wcf_off = S.wcf_off; Q.p_off = S.p_off; Q.col_idx = S.col_idx; Q.row_idx = S.row_idx;
+        Q.ahead = 0;
         LQ.ws = T->ws; LQ.P = P;
         CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
         dsp_ipm_stage2_long_kernel<<<(unsigned)blocks, 32 * wpb, 0, st>>>(LQ);
@@ -1116,6 +1117,7 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
         const stagewb::StageParams &S = T->sp;
         Q.T = S.T; Q.a = S.a; Q.binv = S.binv; Q.hf = S.hf; Q.dl = S.dl; Q.dur = S.dur; Q.krev = S.krev;
         Q.wcf_off = S.wcf_off; Q.p_off = S.p_off; Q.col_idx = S.col_idx; Q.row_idx = S.row_idx;
+        Q.ahead = (int)(blocks * wpb * per_warp);
         CK(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
 #define S2_LAUNCH(l, p)                                                                                      \
         if (sync) dsp_ipm_stage2_wb_kernel<l, p, true><<<(unsigned)blocks, 32 * wpb, smem, st>>>(Q);             \

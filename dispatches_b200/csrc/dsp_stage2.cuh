@@ -59,6 +59,7 @@ struct Params {
     double a, binv, hf, dl, dur, krev;
     int wcf_off, p_off;
     const int *col_idx, *row_idx;
+    int ahead;                 // number of group slots of the launch (L2 prefetch distance in LPs); 0 in the emulator
 };
 
 S2D double frcp(double x) {
@@ -78,6 +79,17 @@ S2D double frcp(double x) {
     return r;
 }
 S2D double dmax(double a, double b) { return a > b ? a : b; }
+// L2 prefetch of `bytes` starting at p, one 128-byte line per lane `l` of the group (inputs of an LP are read once, at its refill,
+// by a group that then waits for them: a DRAM access on the critical path of every round of the CTA unless the lines are in L2)
+S2D void prefetch_l2(const void *p, int bytes, int l) {
+#if defined(__CUDA_ARCH__)
+    int off = l * 128;
+    if (off < bytes + 128) {                       // (every prefetched address lies inside the row: the last lane takes its last byte)
+        if (off > bytes - 1) off = bytes - 1;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)p + off));
+    }
+#endif
+}
 
 // ---- collectives over the L lanes of an LP group (every lane of the warp executes them)
 template <int L>
@@ -355,6 +367,13 @@ __device__ void warp_body(const Params &Q, double *smw, int lane) {
             if (ld) {
                 const double *cp = Q.cparams + p * (long long)Q.Pc;
                 const double *rp = Q.rparams + p * Q.rstride;
+                {   // the LP one wave of group slots ahead: in L2 by the time a group asks for it
+                    const long long pa = p + (long long)Q.ahead;
+                    if (mode == 1 && pa < Q.N) {
+                        prefetch_l2(Q.cparams + pa * (long long)Q.Pc, Q.Pc * 8, gl);
+                        if (Q.rstride) prefetch_l2(Q.rparams + pa * Q.rstride, Q.Pr * 8, gl);
+                    }
+                }
                 for (int r = gl; r < Q.Pr; r += L) kc += Q.omap[r] * rp[r];
                 for (int r = gl; r < Q.Pc; r += L) kc += Q.ocmap[r] * cp[r];
                 Pw = rp[Q.p_off];

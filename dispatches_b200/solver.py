@@ -149,7 +149,7 @@ def _f64(a):
 
 
 class BatchLPSolver:
-    def __init__(self, template: LPTemplate, tol=1e-9, feas_tol=1e-9, max_iter=60, step_frac=0.9995, kernel=KERNEL_AUTO, reg_primal=1e-8,
+    def __init__(self, template: LPTemplate, tol=1e-9, feas_tol=1e-9, max_iter=60, step_frac=0.9995, kernel=KERNEL_AUTO, reg_primal=None,
                  native_setup=False):
         """native_setup=True hands the library the PLAIN standard-form LP (dsp_lp_template_create_csr): column / row ordering and
         the band assembly list are then derived in C++ (what a C caller or the Pyomo walker uses); the default passes the
@@ -211,7 +211,9 @@ class BatchLPSolver:
         self.lib.dsp_lp_default_opts(C.byref(self.opts))
         self.opts.tol, self.opts.feas_tol, self.opts.max_iter, self.opts.step_frac = tol, feas_tol, max_iter, step_frac
         self.opts.kernel = kernel
-        self.opts.reg_primal = reg_primal
+        # proximal term: the library default (1e-8) unless the caller or the template asks otherwise (a template whose feasible set has
+        # no strict interior, e.g. templates.solar_battery_hydrogen, records the value its LPs converge with)
+        self.opts.reg_primal = float(template.meta.get("reg_primal", 1e-8) if reg_primal is None else reg_primal)
         st = t.meta.get("stage_wb")
         self.has_stage = False
         if st is not None and kernel != KERNEL_BAND:

@@ -28,7 +28,7 @@ extern "C" int emu_stage2_solve(int L, int P, int warps, long long N, const doub
     Q.o0 = o0; Q.tol = tol; Q.feas_tol = feas_tol; Q.step_frac = step_frac; Q.reg = reg; Q.max_iter = max_iter;
     Q.obj = obj; Q.x_out = x_out; Q.y_out = y_out; Q.status = status; Q.iters = iters; Q.n = n; Q.m = m; Q.ticket = &ticket;
     Q.T = T; Q.a = a; Q.binv = binv; Q.hf = hf; Q.dl = dl; Q.dur = dur; Q.krev = krev; Q.wcf_off = wcf_off; Q.p_off = p_off;
-    Q.col_idx = col_idx; Q.row_idx = row_idx;
+    Q.col_idx = col_idx; Q.row_idx = row_idx; Q.ahead = 0;
     if (T > L * P) return -1;
 #define CASE(l, p) if (L == l && P == p) { run<l, p>(Q, warps); return 0; }
     CASE(8, 3) CASE(4, 3) CASE(16, 2) CASE(32, 1) CASE(16, 3) CASE(32, 3) CASE(8, 2) CASE(2, 3) CASE(32, 2)
@@ -50,7 +50,7 @@ extern "C" int emu_stage2_long_solve(int warps, long long N, const double *cpara
     Q.o0 = o0; Q.tol = tol; Q.feas_tol = feas_tol; Q.step_frac = step_frac; Q.reg = reg; Q.max_iter = max_iter;
     Q.obj = obj; Q.x_out = x_out; Q.y_out = y_out; Q.status = status; Q.iters = iters; Q.n = n; Q.m = m; Q.ticket = &ticket;
     Q.T = T; Q.a = a; Q.binv = binv; Q.hf = hf; Q.dl = dl; Q.dur = dur; Q.krev = krev; Q.wcf_off = wcf_off; Q.p_off = p_off;
-    Q.col_idx = col_idx; Q.row_idx = row_idx;
+    Q.col_idx = col_idx; Q.row_idx = row_idx; Q.ahead = 0;
     LQ.P = (T + 31) / 32;
     std::vector<double> ws((size_t)warps * stage2long::NW * LQ.P * 32, 0.0);
     LQ.ws = ws.data();
