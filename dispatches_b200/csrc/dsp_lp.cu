@@ -1356,7 +1356,13 @@ static int solve_batch_host_locked(dsp_template *T, int64_t N, const double *cpa
     }
     // templates that run in global-workspace mode share ONE workspace: no concurrent chunk kernels for them
     const bool ws_template = band_geometry(T, K).ws || (T->has_stage && T->sp.T > kStage2MaxT);    // (the long stage kernel's workspace too)
-    const int nchunk = ws_template ? 1 : (int)std::min<int64_t>(in_pinned ? 2 : 8, std::max<int64_t>(1, N / 2048));
+    // Chunks pay when there is something to overlap: the staging memcpy of pageable input (always), or the H2D copy of a batch whose
+    // kernel runs for many waves.  A page-locked batch of a few waves goes in ONE piece: the persistent stage kernels fill every SM
+    // with one CTA, so two chunk kernels cannot share the chip and each chunk ends in its own thinning tail (C2 from pinned
+    // buffers: 0.665 ms in two chunks of 5 000 LPs, ~0.60 ms in one -- H2D 1.9 MB + 0.535 ms kernel + D2H).
+    const int nchunk = ws_template ? 1
+                     : in_pinned   ? (int)std::min<int64_t>(4, std::max<int64_t>(1, N / 65536))
+                                   : (int)std::min<int64_t>(8, std::max<int64_t>(1, N / 2048));
     const int64_t per = (N + nchunk - 1) / nchunk;
     for (int c = 0; c < nchunk; ++c) {
         const int64_t lo = c * per, cnt = std::min<int64_t>(per, N - lo);

@@ -559,6 +559,28 @@ def test_long_horizon_wind_battery_quarter_year():
     assert rel_err(res.obj, ref).max() < REL
 
 
+def test_full_year_wind_battery_on_the_long_horizon_kernel():
+    """the reference's real sweep LP (run_pricetaker_wind_battery.py:57-58: n_time_points = 8736) on the AUTO path: long-horizon stage
+    kernel (one warp per LP, partitioned elimination, state in the workspace) with the band kernel re-solving what it leaves
+    non-optimal -- against the band kernel alone on every LP and against the oracle on one"""
+    import torch
+    p = SC.pool()
+    T, N = 8736, 8
+    t = TP.wind_battery(T)
+    lam, cf = p["dalmp_303"][:T], p["dacf_303"][:T]
+    wind = np.linspace(200.0, 1600.0, N); batt = wind * np.linspace(0.05, 1.0, N)[::-1]
+    rp = torch.tensor(TP.wind_battery_rparams(T, np.tile(cf, (N, 1)), wind, batt), device="cuda")
+    cp = torch.tensor(np.tile(lam, (N, 1)), device="cuda")
+    auto = S.BatchLPSolver(t).solve(cp, rp)
+    band = S.BatchLPSolver(t, kernel=S.KERNEL_BAND).solve(cp, rp)
+    torch.cuda.synchronize()
+    assert int((auto.status != 0).sum()) == 0 and int((band.status != 0).sum()) == 0
+    a, b = auto.obj.cpu().numpy(), band.obj.cpu().numpy()
+    assert rel_err(a, b).max() < 1e-8
+    ref = H.solve(L.wind_battery_raw(lam, cf, wind[2], batt[2]))[0]
+    assert abs(a[2] - ref) / max(1.0, abs(ref)) < REL
+
+
 def test_determinism_and_permutation_invariance(wb):
     """Size-independent properties at the full C2 size: the ticket dispatcher hands LPs to warps in a run-dependent
     order, yet every LP's result depends on its own data only -- two runs agree bit for bit, and permuting the batch
