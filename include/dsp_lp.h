@@ -78,7 +78,10 @@ enum { DSP_KERNEL_AUTO = 0, DSP_KERNEL_BAND = 1, DSP_KERNEL_STAGE = 2 /* generat
        DSP_KERNEL_STAGE_V1 = 3 /* generation 1: lane per period, T <= 32 (kept as an independent implementation for tests) */ };
 
 /* Stage descriptor of the wind+battery price-taker flowsheet (wind_battery_LMP.py:172-267, reduced form):
- * any T (T <= 96: on chip, several LPs per warp; longer: one warp per LP with its state in a workspace), per period the columns g,i,o,s,e,p,q and rows r1 (state_evolution, battery.py:145-149),
+ * any T (T <= 96: on chip, several LPs per warp; longer, up to the reference's full-year 8736 periods of
+ * run_pricetaker_wind_battery.py:57-58: one warp per LP with its state in a workspace owned by the handle -- csrc/dsp_stage2_long.cuh --
+ * followed on the same stream by the band kernel in a retry mode that re-solves only the LPs left non-optimal, so the two launches
+ * count as two in dsp_lp_launch_count), per period the columns g,i,o,s,e,p,q and rows r1 (state_evolution, battery.py:145-149),
  * r2 (accumulate_energy_throughput :151-153), r3 (state_of_charge_bounds :155-157, slack p),
  * r4 (wind_power.py:120-122 + splitter, slack q).  Lets dsp_lp_solve_batch run the stage kernels (several LPs per warp,
  * iterate in registers, partitioned block elimination: csrc/dsp_stage2.cuh) instead of the generic band kernel; results
@@ -160,7 +163,9 @@ int dsp_lp_solve_batch(const dsp_template *t, int64_t N,
 
 /* Same with HOST pointers: pinned staging, H2D of the parameters, kernel, D2H of the results, one sync.
  * This is the call the Pyomo plugin / sweep drivers make; bench.py's "e2e" number times it.
- * Page-locked caller buffers are DMA'd directly (no staging copy).  Not re-entrant per template handle: the staging
+ * Page-locked caller buffers are DMA'd directly (no staging copy) and go to the GPU in one piece unless the batch exceeds 65 536
+ * LPs (then up to 4 chunks on two streams: the copy of one overlaps the kernel of the other); pageable buffers are staged in up to
+ * 8 chunks so that the host memcpy overlaps too.  Not re-entrant per template handle: the staging
  * buffers and streams belong to the handle -- use one handle per host thread; a second concurrent call on the same
  * handle returns DSP_E_BUSY.                                                                            */
 int dsp_lp_solve_batch_host(dsp_template *t, int64_t N,

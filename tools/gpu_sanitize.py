@@ -30,4 +30,10 @@ print("band fossil T=168", int((r.status == 0).sum()), "/", len(r.status), S.las
 p = SC.pool()
 T = 672
 r = S.BatchLPSolver(TP.wind_battery(T)).solve_host(np.tile(p["dalmp_303"][:T], (2, 1)), TP.wind_battery_rparams(T, p["dacf_303"][:T], 847.0, 211.75)[0])
+print("long-horizon stage kernel T=672 (+ retry pass of the band kernel)", int((r.status == 0).sum()), "/", len(r.status), S.last_launch())
+r = S.BatchLPSolver(TP.wind_battery(T), kernel=S.KERNEL_BAND).solve_host(np.tile(p["dalmp_303"][:T], (2, 1)), TP.wind_battery_rparams(T, p["dacf_303"][:T], 847.0, 211.75)[0])
 print("band ws T=672", int((r.status == 0).sum()), "/", len(r.status), S.last_launch())
+ts = TP.solar_battery_hydrogen(24, batt_mw=50.0, batt_mwh=200.0, pem_mw=20.0)
+cfs = np.sin(np.deg2rad(np.linspace(0, 180, 24)))
+r = S.BatchLPSolver(ts).solve_host(np.abs(lmp[:16]) * 0.5, TP.solar_rparams(24, cfs, 200.0, np.full(24, 100.0))[0], want_x=True, want_y=True)
+print("band<16> solar (cyclic)", int((r.status == 0).sum()), "/", len(r.status), S.last_launch())
