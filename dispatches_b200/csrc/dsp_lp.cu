@@ -1346,14 +1346,6 @@ static int solve_batch_host_locked(dsp_template *T, int64_t N, const double *cpa
     if (rc) return rc;
     cudaStream_t sts[2] = {T->stream, T->stream2};
     int64_t dstride = 0;
-    const bool shared_rp = (K.Pr > 0 && rparams_stride == 0);
-    if (shared_rp) {
-        memcpy(T->h_rp, rparams, (size_t)K.Pr * 8);
-        CK(cudaMemcpyAsync(T->d_rp, T->h_rp, (size_t)K.Pr * 8, cudaMemcpyHostToDevice, sts[0]));
-        CK(cudaStreamSynchronize(sts[0]));          // 0.2 KB, makes the row visible to both streams
-    } else if (K.Pr > 0) {
-        dstride = K.Pr;
-    }
     // templates that run in global-workspace mode share ONE workspace: no concurrent chunk kernels for them
     const bool ws_template = band_geometry(T, K).ws || (T->has_stage && T->sp.T > kStage2MaxT);    // (the long stage kernel's workspace too)
     // Chunks pay when there is something to overlap: the staging memcpy of pageable input (always), or the H2D copy of a batch whose
@@ -1363,6 +1355,14 @@ static int solve_batch_host_locked(dsp_template *T, int64_t N, const double *cpa
     const int nchunk = ws_template ? 1
                      : in_pinned   ? (int)std::min<int64_t>(4, std::max<int64_t>(1, N / 65536))
                                    : (int)std::min<int64_t>(8, std::max<int64_t>(1, N / 2048));
+    const bool shared_rp = (K.Pr > 0 && rparams_stride == 0);
+    if (shared_rp) {
+        memcpy(T->h_rp, rparams, (size_t)K.Pr * 8);
+        CK(cudaMemcpyAsync(T->d_rp, T->h_rp, (size_t)K.Pr * 8, cudaMemcpyHostToDevice, sts[0]));
+        if (nchunk > 1) CK(cudaStreamSynchronize(sts[0]));          // 0.2 KB, makes the row visible to both streams (one chunk: stream order suffices)
+    } else if (K.Pr > 0) {
+        dstride = K.Pr;
+    }
     const int64_t per = (N + nchunk - 1) / nchunk;
     for (int c = 0; c < nchunk; ++c) {
         const int64_t lo = c * per, cnt = std::min<int64_t>(per, N - lo);

@@ -620,7 +620,12 @@ __device__ void warp_body_long(const LongParams &LQ, int warp_global, int lane) 
         if ((long long)t >= LQ.q.N) break;
         int it0 = 0;
         for (int attempt = 0; attempt < 2; ++attempt) {
-            const double sf = attempt ? 0.99 : LQ.q.step_frac, rg = attempt ? 10.0 * LQ.q.reg : LQ.q.reg;
+            // second attempt: shorter step and a 100x proximal term (the other kernels use 10x).  At T = 8736 the failures are LPs whose
+            // normal matrix (cond > 1e15) lets the solve drift along near-null directions: dx = D (A' dy - h) with D = x / z ~ 1e9 turns a
+            // 1e-9 error of A' dy into a step of order 1, which the proximal term converts into a dual residual stuck at 1e-7; 1e-6
+            // damps that (emulator and B200: the one LP in 64 of the full-year sweep that 10x leaves NUMERICAL converges, 43 + 55
+            // iterations, objective 4e-12 from the band kernel's; 1000x stalls at MAX_ITER)
+            const double sf = attempt ? 0.99 : LQ.q.step_frac, rg = attempt ? 100.0 * LQ.q.reg : LQ.q.reg;
             const int r = solve_long(LQ, wsw, (long long)t, lane, sf, rg, it0);
             if (r == 0) break;
             it0 = r - 1;

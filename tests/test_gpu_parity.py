@@ -175,6 +175,13 @@ def test_edge_cases(wb):
     r = sol.solve_host(lmp[None], rp0)
     ref0 = H.solve(L.wind_battery_raw(lmp, cf, W, 0.0))[0]
     assert r.status[0] == S.OPTIMAL and rel_err(r.obj[0], ref0) < REL
+    # NaN / infinite prices: NUMERICAL for those LPs only (stage kernel and band kernel), their warp neighbours are unaffected
+    bad = np.stack([lmp, lmp, lmp, lmp, 2.0 * lmp])
+    bad[1, 5] = np.nan; bad[3, 0] = np.inf
+    for solver in (sol, S.BatchLPSolver(t, kernel=S.KERNEL_BAND)):
+        r = solver.solve_host(bad, rp)
+        assert r.status.tolist() == [S.OPTIMAL, 2, S.OPTIMAL, 2, S.OPTIMAL] and np.isnan(r.obj[[1, 3]]).all()
+        assert r.obj[2] == r.obj[0] and rel_err(r.obj[0], ref[3]) < REL
 
 
 def test_device_and_host_paths_agree_and_count_launches(wb):

@@ -102,6 +102,13 @@ def test_edge_cases(emu):
     # the second attempt: an iteration cap forces attempt 1 (shorter step, stronger proximal term) and both counts add up
     obj, status, iters, _, _ = emu.solve(t, lmp[:5], rp, 8, 3, max_iter=6)
     assert (status != 0).all() and (iters == 6 + 6).all()
+    # NaN / infinite prices end as NUMERICAL without disturbing the LPs that share their warp; all-negative prices are a regular LP
+    bad = lmp[:6].copy()
+    bad[1, 5] = np.nan; bad[3, 0] = np.inf; bad[4, :] = -50.0
+    obj, status, iters, _, _ = emu.solve(t, bad, rp, 8, 3)
+    assert status.tolist() == [0, 2, 0, 2, 0, 0] and np.isnan(obj[[1, 3]]).all()
+    ref = np.array([H.solve(L.wind_battery_raw(bad[k], cf, W, P))[0] for k in (0, 2, 4, 5)])
+    assert rel_err(obj[[0, 2, 4, 5]], ref).max() < 1e-7
     # empty batch and a single LP (three of the four groups never get work)
     obj, status, _, _, _ = emu.solve(t, np.zeros((0, 24)), rp, 8, 3)
     assert obj.size == 0
