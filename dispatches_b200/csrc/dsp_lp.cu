@@ -549,7 +549,10 @@ namespace {
 constexpr int kStage2Warps = DSP_S2_WARPS;        // warps per CTA = per SM: 8 x 27.9 KB of shared memory, 8 x 32 x 255 registers.  (9 warps would
                                                  // make a 10 000-LP batch two waves instead of three, but the register file is per scheduler:
                                                  // a third warp on one of the four caps every thread at 168 registers -- 2 KB of spills)
-constexpr int kChain1Warps = 8;
+// warps per CTA (= per SM) of the chain kernel: what shared memory allows at 168 registers per thread (three warps on a scheduler).
+// NF = 2 (19.5 KB per warp): 11 warps -- 3 256 group slots at L = 16, so the 5 000 LPs of C3 are two waves instead of the three
+// they were at 8 warps / 219 registers (0.42 -> see profiles/chain1_warps_r2.log); NF = 3 (24.8 KB per warp): 8
+constexpr int chain1_warps(int NF) { return NF == 2 ? 11 : 8; }
 template <int L, int P, bool SYNC>
 __global__ void __launch_bounds__(32 * kStage2Warps, 1) dsp_ipm_stage2_wb_kernel(const stage2::Params Q) {
     extern __shared__ __align__(16) double s2_smem[];
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(32 * kStage2Warps, 1) dsp_ipm_stage2_wb_kernel
 namespace {
 // descriptor-driven stage kernel of the single-storage-chain family (dsp_stage_chain1.cuh): same CTA shape as stage2
 template <int L, int P, int NF>
-__global__ void __launch_bounds__(32 * kChain1Warps, 1) dsp_ipm_stage_chain1_kernel(const chain1::Params Q) {
+__global__ void __launch_bounds__(32 * chain1_warps(NF), 1) dsp_ipm_stage_chain1_kernel(const chain1::Params Q) {
     extern __shared__ __align__(16) double s2_smem[];
     chain1::warp_body<L, P, NF, true>(Q, s2_smem + (threadIdx.x >> 5) * chain1::Smem<NF, P>::doubles_per_warp, threadIdx.x & 31);
 }
@@ -963,7 +966,7 @@ int dsp_lp_template_set_stage_chain1(dsp_template *T, const dsp_stage_chain1_des
     T->c1_T = d->T; T->c1_NF = d->NF;
     T->c1_col_idx = dci; T->c1_row_idx = dri; T->c1_coef = dcf; T->c1_coef_next = dcn;
     const int L = chain1_lanes(d->T);
-    const size_t smem = (size_t)(T->c1_NF == 2 ? chain1::Smem<2, 3>::doubles_per_warp : chain1::Smem<3, 3>::doubles_per_warp) * 8 * kChain1Warps;
+    const size_t smem = (size_t)(T->c1_NF == 2 ? chain1::Smem<2, 3>::doubles_per_warp : chain1::Smem<3, 3>::doubles_per_warp) * 8 * chain1_warps(T->c1_NF);
 #define C1_ATTR(l, nf) do { CK(cudaFuncSetAttribute(dsp_ipm_stage_chain1_kernel<l, 3, nf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
                             CK(cudaFuncSetAttribute(dsp_ipm_stage_chain1_kernel<l, 3, nf>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); } while (0)
     if (T->c1_NF == 2) { if (L == 4) C1_ATTR(4, 2); else if (L == 8) C1_ATTR(8, 2); else if (L == 16) C1_ATTR(16, 2); else C1_ATTR(32, 2); }
@@ -1147,8 +1150,8 @@ static int launch_batch(const dsp_template *T, int64_t N, const double *cparams,
     }
     if (!K.retry_only && T->has_chain1 && (o.kernel == DSP_KERNEL_AUTO || o.kernel == DSP_KERNEL_STAGE)) {
         const int L = chain1_lanes(T->c1_T), per_warp = 32 / L, NF = T->c1_NF;
-        int wmax = kChain1Warps;
-        if (const char *e = getenv("DSP_STAGE2_WARPS")) wmax = std::min(kChain1Warps, std::max(1, atoi(e)));
+        int wmax = chain1_warps(NF);
+        if (const char *e = getenv("DSP_CHAIN1_WARPS")) wmax = std::min(wmax, std::max(1, atoi(e)));      // experiments only
         const long long warps_needed = (N + per_warp - 1) / per_warp;
         const long long blocks = std::max<long long>(1, std::min<long long>(T->sm_count, warps_needed));
         const int wpb = (int)std::min<long long>(wmax, (warps_needed + blocks - 1) / blocks);
