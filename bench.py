@@ -108,8 +108,14 @@ CONFIG_DEFS = {
                     "structure-only, parity vs HiGHS on the surrogate, NOT vs the reference's IPOPT objective (parity unpinned)"),
     "C5": dict(kind="wind_battery", T=24, N=560640,
                what="design sweep: 64 design points x 8 760 hourly 24-h windows = 560 640 LPs, cost AND rhs batched"),
+    # not a BASELINE.json config: the sweep the reference's driver really runs (run_pricetaker_wind_battery.py:37-58 solves ONE
+    # full-year LP, n_time_points = 8736, per design point) -- the long-horizon stage kernel (csrc/dsp_stage2_long.cuh)
+    "FY": dict(kind="wind_battery", T=8736, N=64,
+               what="the reference's own sweep: 8 wind sizes x 8 battery ratios, one FULL-YEAR 8736-period LP per design point "
+                    "(303 DA prices / capacity factors), long-horizon stage kernel"),
 }
-CPU_SAMPLE_PER_CORE = {"C3": 96, "C4": 24, "C5": 96}
+CPU_SAMPLE_PER_CORE = {"C3": 96, "C4": 24, "C5": 96, "FY": 1}
+CPU_SAMPLE_FIXED = {"FY": [9, 27, 36, 50]}     # full-year LPs cost HiGHS ~7 s each: four fixed design points (one process each)
 
 
 def config_data(name):
@@ -119,6 +125,14 @@ def config_data(name):
         return (lambda: TP.nuclear(48)), SC.c3(5000), None, None
     if name == "C4":
         return (lambda: TP.fossil_surrogate(168)), SC.c4(2000), None, None
+    if name == "FY":
+        p = SC.pool()
+        Tf = CONFIG_DEFS["FY"]["T"]
+        lam, cf1 = p["dalmp_303"][:Tf], p["dacf_303"][:Tf]
+        w = np.repeat(np.linspace(200.0, 1600.0, 8), 8)
+        b = np.tile(np.linspace(0.05, 1.0, 8), 8) * w
+        cf = np.tile(cf1, (64, 1))
+        return (lambda: TP.wind_battery(Tf)), np.tile(lam, (64, 1)), TP.wind_battery_rparams(Tf, cf, w, b), (cf, w, b)
     lmp, cf, w, b = SC.c5()
     return (lambda: TP.wind_battery(24)), lmp, TP.wind_battery_rparams(24, cf, w, b), (cf, w, b)
 
@@ -126,6 +140,8 @@ def config_data(name):
 def config_sample(name, cores):
     """seeded sample of a config's LP indices for the parity check / CPU baseline"""
     N = CONFIG_DEFS[name]["N"]
+    if name in CPU_SAMPLE_FIXED:
+        return np.array(CPU_SAMPLE_FIXED[name][:max(1, min(len(CPU_SAMPLE_FIXED[name]), cores))])
     n = int(min(N, CPU_SAMPLE_PER_CORE[name] * cores))
     return np.sort(np.random.default_rng(777).choice(N, n, replace=False))
 
@@ -137,10 +153,10 @@ def cpu_config_run(name, procs=None):
     _, cp, _, extra = config_data(name)
     idx = config_sample(name, procs)
     kind = CONFIG_DEFS[name]["kind"]
-    if name == "C5":
+    if extra is not None:
         cf, w, b = extra
         ex = [(cf[i], float(w[i]), float(b[i])) for i in idx]
-        obj, dt, procs = H.solve_batch(kind, cp[idx], extras=ex, procs=procs)
+        obj, dt, procs = H.solve_batch(kind, cp[idx], extras=ex, procs=min(procs, idx.size))
     else:
         obj, dt, procs = H.solve_batch(kind, cp[idx], procs=procs)
     return idx, obj, dt, procs
@@ -413,15 +429,19 @@ def main():
                     "bench.cpu_reference_run(lmp, cf, W, P, min(n, 16 * c)); ref, dt, procs = bench.cpu_reference_run(lmp, cf, W, P, n); "
                     "out = dict(ref=ref, dt=dt, procs=procs, n=n)\n"
                     "for name in %r:\n"
-                    "    idx, obj, dtc, pr = bench.cpu_config_run(name)\n"
-                    "    out[name + '_idx'] = idx; out[name + '_obj'] = obj; out[name + '_dt'] = dtc\n"
+                    "    try:\n"
+                    "        idx, obj, dtc, pr = bench.cpu_config_run(name)\n"
+                    "        out[name + '_idx'] = idx; out[name + '_obj'] = obj; out[name + '_dt'] = dtc; out[name + '_procs'] = pr\n"
+                    "    except Exception as e:\n"
+                    "        print('cpu baseline of', name, 'failed:', e, file=sys.stderr)\n"
                     "np.savez(%r, **out)") % (str(ROOT), [] if args.no_configs else list(CONFIG_DEFS), outp)
             rc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1500)
             if rc.returncode == 0:
                 z = np.load(outp)
                 cpu = dict(ref=z["ref"], dt=float(z["dt"]), procs=int(z["procs"]), n=int(z["n"]))
                 for name in cfg_res:
-                    cfg_cpu[name] = (z[name + "_idx"], z[name + "_obj"], float(z[name + "_dt"]))
+                    if name + "_idx" in z:
+                        cfg_cpu[name] = (z[name + "_idx"], z[name + "_obj"], float(z[name + "_dt"]), int(z[name + "_procs"]))
             else:
                 line["cpu_baseline"] = {"error": rc.stderr[-300:]}
     if cpu is not None:
@@ -433,11 +453,12 @@ def main():
     for name, r in cfg_res.items():
         obj = r.pop("obj")
         if name in cfg_cpu:
-            idx, ref, dtc = cfg_cpu[name]
+            idx, ref, dtc, prc = cfg_cpu[name]
             r["max_rel_err_vs_oracle"] = float(np.max(np.abs(obj[idx] - ref) / np.maximum(1.0, np.abs(ref))))
-            r["parity_sample"] = f"{idx.size} seeded LPs (rng 777) vs restated LP + HiGHS"
-            r["cpu_baseline"] = {"value": idx.size / dtc, "unit": "LPs/s", "cores": cpu["procs"], "kind": "port",
-                                 "sample": f"{idx.size} LPs of the config, HiGHS dual simplex, {cpu['procs']} processes"}
+            r["parity_sample"] = (f"design points {idx.tolist()} vs restated LP + HiGHS" if name in CPU_SAMPLE_FIXED
+                                  else f"{idx.size} seeded LPs (rng 777) vs restated LP + HiGHS")
+            r["cpu_baseline"] = {"value": idx.size / dtc, "unit": "LPs/s", "cores": prc, "kind": "port",
+                                 "sample": f"{idx.size} LPs of the config, HiGHS dual simplex, {prc} processes"}
             r["vs_cpu"] = r["lps"] / (idx.size / dtc)
         r["obj_checksum"] = float(obj.sum())
     if cfg_res:

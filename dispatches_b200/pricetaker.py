@@ -231,6 +231,9 @@ def pv_battery_hydrogen_optimize(n_time_points, input_params, verbose=False, plo
         raise NotImplementedError("pv_battery_hydrogen_optimize: design_opt=True is not on the batched GPU path "
                                   "(six dense size columns); solve the fixed-design LP per candidate size instead")
     T = int(n_time_points)
+    for k in ("LMP", "pv_resource", "load", "reserve", "pv_mw", "tank_size", "turb_mw"):
+        if k not in input_params:
+            raise KeyError(f"pv_battery_hydrogen_optimize: input_params[{k!r}] is required")
     lmp = np.ascontiguousarray(np.atleast_2d(np.asarray(input_params["LMP"], float))[:, :T])
     pr = input_params["pv_resource"]
     if isinstance(pr, dict):       # the reference's {t: {'pv_resource_config': {'capacity_factor': cf}}}
@@ -238,6 +241,11 @@ def pv_battery_hydrogen_optimize(n_time_points, input_params, verbose=False, plo
     else:
         cfs = np.asarray(pr, float)[..., :T]
     load = np.asarray(input_params["load"], float)[..., :T]
+    for name, a in (("LMP", lmp), ("pv_resource", cfs), ("load", load), ("reserve", np.asarray(input_params["reserve"], float)[..., :T])):
+        if a.shape[-1] != T or a.ndim > 2 or (name == "reserve" and a.ndim != 1):
+            raise ValueError(f"pv_battery_hydrogen_optimize: {name} must provide {T} values per scenario (reserve: one series), got shape {a.shape}")
+    if np.any(cfs < 0) or not np.all(np.isfinite(cfs)) or not np.all(np.isfinite(load)):
+        raise ValueError("pv_battery_hydrogen_optimize: capacity factors must be finite and >= 0, loads finite")
     batt_mw = float(input_params.get("batt_mw", 0.0))
     batt_mwh = float(input_params["batt_mw"] * input_params["batt_hr"]) if "batt_hr" in input_params else float(input_params.get("batt_mwh", 0.0))
     par = {k: float(input_params[k]) for k in _SOLAR_COST_KEYS if k in input_params}

@@ -147,6 +147,11 @@ def check_reference_shaped_api():
     params["design_opt"] = True
     with pytest.raises(NotImplementedError):
         PT.pv_battery_hydrogen_optimize(24, params)
+    params["design_opt"] = False
+    with pytest.raises(ValueError):
+        PT.pv_battery_hydrogen_optimize(24, {**params, "load": np.ones(12)})            # too short
+    with pytest.raises(KeyError):
+        PT.pv_battery_hydrogen_optimize(24, {k: v for k, v in params.items() if k != "reserve"})
 
 
 @pytest.mark.gpu
