@@ -1,0 +1,1 @@
+"""TEST INFRASTRUCTURE -- NOT idaes-pse: see multiperiod/multiperiod.py"""

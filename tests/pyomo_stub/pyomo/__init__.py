@@ -3,7 +3,7 @@
 where Pyomo cannot be installed (no network, not in /opt/wheelhouse).  tests/test_pyomo_plugin.py puts this directory on
 sys.path only when `import pyomo` fails; with the real package present the same tests run against it.
 
-Covered: ConcreteModel / Block (scalar + indexed) / Var / Param(mutable) / Constraint (expr= or indexed rule=) / Objective /
+Covered: ConcreteModel / Block (scalar + indexed, clone()) / Set / RangeSet / Var / Param(mutable) / Constraint (expr= or indexed rule=) / Objective /
 Expression / Suffix, linear expression algebra with lazily evaluated Params, component_data_objects, value(),
 repn.generate_standard_repn, opt.SolverFactory / SolverResults / SolverStatus / TerminationCondition.
 """

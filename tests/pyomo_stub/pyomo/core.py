@@ -123,6 +123,36 @@ class Component:
     def deactivate(self): self.active = False
     def activate(self): self.active = True
 
+    def __deepcopy__(self, memo):
+        # several component classes dispatch in __new__ (scalar vs indexed): copy the instance without going through it
+        import copy
+        cls = type(self)
+        if isinstance(self, list):
+            new = list.__new__(cls); memo[id(self)] = new
+            list.extend(new, [copy.deepcopy(v, memo) for v in self])
+        elif isinstance(self, dict):
+            new = dict.__new__(cls); memo[id(self)] = new
+            dict.update(new, {copy.deepcopy(k, memo): copy.deepcopy(v, memo) for k, v in self.items()})
+        else:
+            new = object.__new__(cls); memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            object.__setattr__(new, k, copy.deepcopy(v, memo))
+        return new
+
+
+class Set(Component, list):
+    """an ordered index set: ``m.TIME = Set(initialize=range(T))``; usable wherever the stub takes an index"""
+    def __init__(self, initialize=(), doc=None, ordered=True):
+        Component.__init__(self)
+        list.__init__(self, initialize)
+    __hash__ = object.__hash__
+    def first(self): return self[0]
+    def last(self): return self[-1]
+
+
+def RangeSet(*a):
+    return Set(initialize=range(*a) if len(a) > 1 else range(1, a[0] + 1))
+
 
 class IndexedMixin:
     def _make_index(self, index):
@@ -343,6 +373,13 @@ class BlockData(Component):
             setattr(self, f.__name__, c)
             return c
         return deco
+
+    def clone(self):
+        """deep copy of the block tree (what wind_battery_mp_block does with its cached one-period model, wind_battery_LMP.py:159-161)"""
+        import copy
+        c = copy.deepcopy(self)
+        object.__setattr__(c, "_parent", None)
+        return c
 
     def component_data_objects(self, ctype, active=None, descend_into=True):
         for comp in self._components:
