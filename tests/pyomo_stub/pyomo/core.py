@@ -114,11 +114,21 @@ class Component:
     ctype = None
 
     def __init__(self):
-        self.name, self.active, self._parent = None, True, None
+        self.name, self.active, self._parent, self._local_name = None, True, None, None
 
     def _attach(self, parent, name):
         self._parent = parent
-        self.name = name if parent is None or parent.name in (None, "") or isinstance(parent, ConcreteModel) else f"{parent.name}.{name}"
+        self._local_name = name
+        self._rename()
+
+    def _rename(self):
+        """hierarchical name from the parent chain; re-run for a whole subtree when a pre-built model is attached as a sub-block
+        (MultiPeriodModel: blocks[t].process = <clone of the one-period flowsheet>), as Pyomo's lazily computed names would give"""
+        parent, name = self._parent, self._local_name
+        self.name = name if parent is None or parent.name in (None, "") else f"{parent.name}.{name}"
+        for i, d in (getattr(self, "_data", None) or {}).items():
+            if not isinstance(d, BlockData):
+                d.name = f"{self.name}[{i}]"
 
     def deactivate(self): self.active = False
     def activate(self): self.active = True
@@ -305,13 +315,13 @@ class Constraint(Component, IndexedMixin):
         self._rule = rule
 
     def _attach(self, parent, name):
-        Component._attach(self, parent, name)
+        self._parent, self._local_name = parent, name
         for i in self._index:
             rel = self._rule(parent, i)
             if rel is Constraint.Skip:
                 continue
             self._data[i] = ConstraintData(rel)
-            self._data[i].name = f"{self.name}[{i}]"
+        self._rename()
 
 
 class ScalarConstraint(ConstraintData, Component):
@@ -364,8 +374,10 @@ class BlockData(Component):
             self._components.append(v)
         object.__setattr__(self, k, v)
 
-    def _attach(self, parent, name):
-        Component._attach(self, parent, name)
+    def _rename(self):
+        Component._rename(self)
+        for comp in self._components:
+            comp._rename()
 
     def Constraint(self, *index, doc=None):              # decorator form  @m.Constraint(m.set)
         def deco(f):
@@ -413,11 +425,13 @@ class Block(Component, IndexedMixin):
         for i in self._index:
             self._data[i] = BlockData()
 
-    def _attach(self, parent, name):
-        Component._attach(self, parent, name)
+    def _rename(self):
+        Component._rename(self)
         for i, b in self._data.items():
-            b._parent = parent
+            b._parent = self._parent
             b.name = f"{self.name}[{i}]"
+            for comp in b._components:
+                comp._rename()
 
 
 class ConcreteModel(BlockData):

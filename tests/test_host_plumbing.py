@@ -29,7 +29,8 @@ class HighsStandIn:
             assert r.status == 0, r.message
             objs.append(r.fun + kk); xs.append(r.x)
         n = len(objs)
-        return S.LPResult(np.array(objs), np.zeros(n, np.int32), np.full(n, 10, np.int32), np.array(xs), None)
+        return S.LPResult(np.array(objs), np.zeros(n, np.int32), np.full(n, 10, np.int32), np.array(xs),
+                          np.zeros((n, self.t.m)) if want_y else None)       # (duals are what the gpu tests check)
 
     def to_model_space(self, x):
         return x * self.t.col_scale + self.t.col_shift
@@ -53,6 +54,14 @@ def test_pricetaker_api_plumbing(stand_in, tmp_path):
 def test_solar_api_plumbing(stand_in):
     import test_solar_battery_hydrogen as SB
     SB.check_reference_shaped_api()
+
+
+def test_multiperiod_builder_api_plumbing(stand_in, monkeypatch):
+    """reference-shaped MultiPeriodModel code through SolverFactory("b200ipm").solve(m): Var write-back into the cloned period blocks"""
+    import test_multiperiod_api as MP
+    from dispatches_b200 import pyomo_plugin as PP
+    monkeypatch.setattr(PP, "BatchLPSolver", HighsStandIn)
+    MP.check_reference_shaped_optimize()
 
 
 def test_double_loop_api_plumbing(stand_in):

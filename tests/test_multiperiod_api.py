@@ -168,8 +168,7 @@ def test_reference_shaped_multiperiod_build_walks_to_the_oracle_lp():
         assert obj == pytest.approx(ref, rel=1e-11)
 
 
-@pytest.mark.gpu
-def test_reference_shaped_optimize_runs_on_the_gpu_solver():
+def check_reference_shaped_optimize():
     T = 24
     lmp, cf, W, P = SC.c2(2)
     mp = wind_battery_optimize(T, default_params(T, lmp[1], cf, W, P), "b200ipm")               # ... opt.solve(m) inside
@@ -182,3 +181,10 @@ def test_reference_shaped_optimize_runs_on_the_gpu_solver():
     assert max(soc) <= 4 * P * 1e3 * (1 + 1e-6) and min(soc) >= -1e-3
     assert all(w <= W * 1e3 * cf[i] * (1 + 1e-6) + 1e-3 for i, w in enumerate(wind_gen))
     assert pyo.value(m.annual_revenue) == pytest.approx((pyo.value(m.NPV) + (L.BATT_CAP_COST_KW + 4 * L.BATT_CAP_COST_KWH) * P * 1e3) / L.PA, rel=1e-9)
+    names = [v.name for b in blks for v in (b.fs.battery.elec_out[0], b.fs.splitter.grid_elec[0])]
+    assert len(set(names)) == 2 * T and names[0] == "blocks[0].process.fs.battery.elec_out[0]"       # hierarchical names of the cloned blocks
+
+
+@pytest.mark.gpu
+def test_reference_shaped_optimize_runs_on_the_gpu_solver():
+    check_reference_shaped_optimize()
