@@ -180,7 +180,7 @@ def check_reference_shaped_optimize():
     wind_gen = [pyo.value(blks[i].fs.windpower.electricity[0]) for i in range(T)]
     assert max(soc) <= 4 * P * 1e3 * (1 + 1e-6) and min(soc) >= -1e-3
     assert all(w <= W * 1e3 * cf[i] * (1 + 1e-6) + 1e-3 for i, w in enumerate(wind_gen))
-    assert pyo.value(m.annual_revenue) == pytest.approx((pyo.value(m.NPV) + (L.BATT_CAP_COST_KW + 4 * L.BATT_CAP_COST_KWH) * P * 1e3) / L.PA, rel=1e-9)
+    assert pyo.value(m.annual_revenue) == pytest.approx((pyo.value(m.NPV) + (L.BATT_CAP_COST_KW + 4 * L.BATT_CAP_COST_KWH) * P * 1e3) / L.PA, rel=1e-6)   # (the interior-point battery_system_capacity is tight to ~1e-9)
     names = [v.name for b in blks for v in (b.fs.battery.elec_out[0], b.fs.splitter.grid_elec[0])]
     assert len(set(names)) == 2 * T and names[0] == "blocks[0].process.fs.battery.elec_out[0]"       # hierarchical names of the cloned blocks
 
